@@ -1,0 +1,255 @@
+"""ctypes mirror of include/reina_b200.h.
+
+`Engine` binds one shared library that exports the C-ABI with a given prefix: the product binds
+`libreina_b200.so` (prefix `rb_`, CUDA); tests bind the CPU oracle (`ro_`) through the very same class
+to compare the two on identical inputs.  Nothing in this package ever loads the oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+RB_MAX_AGES = 128
+RB_MAX_VARIANTS = 4
+RB_MAX_ROWS = 96
+RB_MAX_IMPORT_EVENTS = 8
+RB_MAX_VACC = 8
+RB_MAX_IMPORT_CLASSES = 16
+RB_N_PLACES = 6
+RB_IOT_LEN = 21
+RB_N_TABLES = 6
+
+ATTRS = ['susceptible', 'vaccinated', 'infected', 'all_infected', 'detected', 'all_detected',
+         'in_icu', 'cum_icu', 'in_ward', 'dead', 'recovered', 'non_hospital_deaths', 'new_infections']
+RB_N_ATTRS = len(ATTRS)
+SCALARS = ['available_icu_units', 'available_hospital_beds', 'total_icu_units', 'total_hospital_beds',
+           'total_infections', 'total_infectors', 'exposed_per_day', 'ct_cases_per_day', 'table_epoch',
+           'day']
+RB_S_CONTACTS0 = len(SCALARS)
+RB_S_VARIANT0 = RB_S_CONTACTS0 + RB_N_PLACES
+RB_N_SCALARS = RB_S_VARIANT0 + RB_MAX_VARIANTS
+
+T_SUSCEPTIBILITY, T_SYMPTOMATIC, T_SEVERE, T_CRITICAL, T_FATAL, T_DEATH_OUTSIDE_HOSPITAL = range(6)
+
+
+class Variant(C.Structure):
+    _fields_ = [
+        ('p_icu_death_no_beds', C.c_float), ('p_hospital_death_no_beds', C.c_float),
+        ('infectiousness_multiplier', C.c_float), ('p_asymptomatic_infection', C.c_float),
+        ('p_mask_protects_wearer', C.c_float), ('p_mask_protects_others', C.c_float),
+        ('ratio_before_hospitalisation', C.c_float), ('ratio_in_ward', C.c_float),
+        ('incubation_kappa', C.c_float), ('incubation_theta', C.c_float),
+        ('onset_death_kappa', C.c_float), ('onset_death_theta', C.c_float),
+        ('onset_recovery_kappa', C.c_float), ('onset_recovery_theta', C.c_float),
+        ('reserved', C.c_float * 2),
+        ('iot', C.c_float * (RB_IOT_LEN + 3)),
+        ('tab', (C.c_float * RB_MAX_AGES) * RB_N_TABLES),
+    ]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ('n_agents', C.c_int32), ('n_ages', C.c_int32), ('n_groups', C.c_int32),
+        ('n_variants', C.c_int32), ('n_replicas', C.c_int32), ('seed', C.c_uint32),
+        ('hospital_beds', C.c_int32), ('icu_units', C.c_int32), ('max_days', C.c_int32),
+        ('n_import_classes', C.c_int32), ('device', C.c_int32), ('contact_capacity', C.c_float),
+        ('reserved', C.c_int32 * 4),
+    ]
+
+
+class DayParams(C.Structure):
+    _fields_ = [
+        ('testing_mode', C.c_int32), ('p_detected_anyway', C.c_float),
+        ('p_successful_tracing', C.c_float), ('beds_delta', C.c_int32), ('icu_delta', C.c_int32),
+        ('table_epoch', C.c_int32), ('n_imports', C.c_int32),
+        ('import_amount', C.c_int32 * RB_MAX_IMPORT_EVENTS),
+        ('import_variant', C.c_int32 * RB_MAX_IMPORT_EVENTS),
+        ('trickle', C.c_int32 * RB_MAX_VARIANTS), ('n_vacc', C.c_int32),
+        ('vacc_nr', C.c_int32 * RB_MAX_VACC), ('vacc_min_age', C.c_int32 * RB_MAX_VACC),
+        ('vacc_max_age', C.c_int32 * RB_MAX_VACC), ('vacc_slot', C.c_int32 * RB_MAX_VACC),
+        ('reserved', C.c_int32 * 4),
+    ]
+
+
+AGENT_DTYPE = np.dtype([
+    ('infector', '<i4'), ('n_infected', '<i4'), ('days_left', '<i2'), ('day_of_illness', '<i2'),
+    ('day_of_vaccination', '<i2'), ('state', 'u1'), ('severity', 'u1'), ('variant', 'u1'),
+    ('flags', 'u1'), ('ward_days', 'u1'), ('icu_days', 'u1')], align=True)
+assert AGENT_DTYPE.itemsize == 20, AGENT_DTYPE.itemsize
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIB_PATH = os.path.join(_HERE, 'libreina_b200.so')
+
+SYMBOLS = ['create', 'destroy', 'set_contact_table', 'set_schedule', 'step', 'sync', 'day',
+           'snapshot', 'row_len', 'read_stats', 'read_per_age', 'problem', 'sample', 'read_agents',
+           'read_queue', 'read_available', 'last_step_ms', 'launch_count', 'last_error']
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class Library:
+    """A loaded shared library exporting the C-ABI under `prefix`."""
+
+    def __init__(self, path, prefix):
+        if not os.path.exists(path):
+            raise EngineError(
+                '%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                '(there is no CPU fallback)' % path)
+        self.path, self.prefix = path, prefix
+        self.dll = C.CDLL(path)
+        f = {}
+        for name in SYMBOLS:
+            f[name] = getattr(self.dll, prefix + name)   # AttributeError if a symbol is missing
+        vp = C.c_void_p
+        f['create'].argtypes = [C.POINTER(Config), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                C.POINTER(Variant), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                C.POINTER(C.c_float), C.POINTER(vp)]
+        f['destroy'].argtypes = [vp]
+        f['destroy'].restype = None
+        f['set_contact_table'].argtypes = [vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_uint8), C.POINTER(C.c_float),
+                                           C.POINTER(C.c_double)]
+        f['set_schedule'].argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(DayParams)]
+        f['step'].argtypes = [vp, C.c_int32]
+        f['sync'].argtypes = [vp]
+        f['day'].argtypes = [vp]
+        f['day'].restype = C.c_int32
+        f['snapshot'].argtypes = [vp]
+        f['row_len'].argtypes = [vp]
+        f['row_len'].restype = C.c_int32
+        f['read_stats'].argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+        f['read_per_age'].argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+        f['problem'].argtypes = [vp, C.POINTER(C.c_int32)]
+        f['sample'].argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+        f['read_agents'].argtypes = [vp, C.c_int32, C.c_void_p]
+        f['read_queue'].argtypes = [vp, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
+        f['read_available'].argtypes = [vp, C.c_int32, C.POINTER(C.c_int32)]
+        f['last_step_ms'].argtypes = [vp]
+        f['last_step_ms'].restype = C.c_float
+        f['launch_count'].argtypes = [vp]
+        f['launch_count'].restype = C.c_int64
+        f['last_error'].argtypes = []
+        f['last_error'].restype = C.c_char_p
+        self.f = f
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise EngineError('%s%s failed (%d): %s' % (
+                self.prefix, what, rc, (self.f['last_error']() or b'').decode(errors='replace')))
+
+
+_cuda_lib = None
+
+
+def cuda_library():
+    """The product library.  Raises if it has not been built -- there is no CPU fallback."""
+    global _cuda_lib
+    if _cuda_lib is None:
+        _cuda_lib = Library(CUDA_LIB_PATH, 'rb_')
+    return _cuda_lib
+
+
+class Engine:
+    """Thin object wrapper over one engine handle."""
+
+    def __init__(self, lib, cfg, age_counts, group_of_age, variants, import_lo, import_hi, import_cum):
+        self.lib = lib
+        self.cfg = cfg
+        self.n_agents, self.n_ages = cfg.n_agents, cfg.n_ages
+        self.n_groups, self.n_replicas = cfg.n_groups, cfg.n_replicas
+        age_counts = np.ascontiguousarray(age_counts, dtype=np.int32)
+        group_of_age = np.ascontiguousarray(group_of_age, dtype=np.int32)
+        import_lo = np.ascontiguousarray(import_lo, dtype=np.int32)
+        import_hi = np.ascontiguousarray(import_hi, dtype=np.int32)
+        import_cum = np.ascontiguousarray(import_cum, dtype=np.float32)
+        varr = (Variant * len(variants))(*variants)
+        h = C.c_void_p()
+        lib.check(lib.f['create'](C.byref(cfg), _ptr(age_counts, C.c_int32), _ptr(group_of_age, C.c_int32),
+                                  varr, _ptr(import_lo, C.c_int32), _ptr(import_hi, C.c_int32),
+                                  _ptr(import_cum, C.c_float), C.byref(h)), 'create')
+        self.h = h
+        self.row_len = lib.f['row_len'](h)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.f['destroy'](self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_contact_table(self, epoch, t):
+        f = self.lib.f['set_contact_table']
+        self.lib.check(f(self.h, epoch, _ptr(t['n_rows'], C.c_int32), _ptr(t['cum_p'], C.c_double),
+                         _ptr(t['age_lo'], C.c_int32), _ptr(t['age_hi'], C.c_int32),
+                         _ptr(t['place'], C.c_uint8), _ptr(t['mask_p'], C.c_float),
+                         _ptr(t['nr_contacts'], C.c_double)), 'set_contact_table')
+
+    def set_schedule(self, day0, params):
+        arr = (DayParams * len(params))(*params)
+        self.lib.check(self.lib.f['set_schedule'](self.h, day0, len(params), arr), 'set_schedule')
+
+    def step(self, n=1):
+        self.lib.check(self.lib.f['step'](self.h, n), 'step')
+
+    def sync(self):
+        self.lib.check(self.lib.f['sync'](self.h), 'sync')
+
+    def day(self):
+        return self.lib.f['day'](self.h)
+
+    def snapshot(self):
+        self.lib.check(self.lib.f['snapshot'](self.h), 'snapshot')
+
+    def read_stats(self, day0, n):
+        out = np.empty((self.n_replicas, n, self.row_len), dtype=np.int32)
+        self.lib.check(self.lib.f['read_stats'](self.h, day0, n, _ptr(out, C.c_int32)), 'read_stats')
+        return out
+
+    def read_per_age(self, replica, attr):
+        out = np.empty(self.n_ages, dtype=np.int32)
+        self.lib.check(self.lib.f['read_per_age'](self.h, replica, attr, _ptr(out, C.c_int32)), 'read_per_age')
+        return out
+
+    def problem(self):
+        out = np.zeros(self.n_replicas, dtype=np.int32)
+        self.lib.check(self.lib.f['problem'](self.h, _ptr(out, C.c_int32)), 'problem')
+        return out
+
+    def sample(self, what, age, severity, n=10000):
+        out = np.empty(n, dtype=np.int32)
+        self.lib.check(self.lib.f['sample'](self.h, what, age, severity, n, _ptr(out, C.c_int32)), 'sample')
+        return out
+
+    def read_agents(self, replica=0):
+        out = np.empty(self.n_agents, dtype=AGENT_DTYPE)
+        self.lib.check(self.lib.f['read_agents'](self.h, replica, out.ctypes.data), 'read_agents')
+        return out
+
+    def read_queue(self, replica=0):
+        cap = max(1024, self.n_agents)
+        out = np.empty(cap, dtype=np.int32)
+        n = C.c_int32()
+        self.lib.check(self.lib.f['read_queue'](self.h, replica, _ptr(out, C.c_int32), cap, C.byref(n)), 'read_queue')
+        return out[:n.value].copy()
+
+    def read_available(self, replica=0):
+        out = np.zeros(2, dtype=np.int32)
+        self.lib.check(self.lib.f['read_available'](self.h, replica, _ptr(out, C.c_int32)), 'read_available')
+        return out
+
+    def last_step_ms(self):
+        return float(self.lib.f['last_step_ms'](self.h))
+
+    def launch_count(self):
+        return int(self.lib.f['launch_count'](self.h))

@@ -1,0 +1,59 @@
+"""Generate golden ensemble statistics from the UNMODIFIED reference engine (oracle/_ref).
+
+Run in the build container (where oracle/build_ref.sh can build the reference):
+    python tests/golden/make_golden.py [--seeds 64] [--configs ...]
+Writes tests/golden/ref_ensemble_<config>.npz with, per (day, series): mean, sample std (ddof=1)
+and n over the seeds, plus the series names.  These files pin the statistical parity tests
+(north_star: every daily series within 3 standard errors over >= 64 seeds per side).
+
+The reference has no golden vectors of its own for this path ("parity
+unpinned"), so outputs of the reference itself are the pin.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness  # noqa: E402
+
+CONFIGS = {
+    # name: (area, scenario, days)
+    'varsinais_suomi_default': ('Varsinais-Suomi', None, 180),
+    'hus_default': ('HUS', None, 180),
+    'hus_hammer_and_dance': ('HUS', 'hammer-and-dance', 180),
+    'hus_mitigation': ('HUS', 'mitigation', 180),
+    'hus_summer_boogie': ('HUS', 'summer-boogie', 180),
+    'hus_looser_restrictions': ('HUS', 'looser-restrictions-to-start-with', 180),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--seeds', type=int, default=64)
+    ap.add_argument('--seed0', type=int, default=1000)
+    ap.add_argument('--processes', type=int, default=None)
+    ap.add_argument('--configs', nargs='*', default=list(CONFIGS))
+    a = ap.parse_args()
+    for name in a.configs:
+        area, scenario, days = CONFIGS[name]
+        t0 = time.time()
+        seeds = np.arange(a.seed0, a.seed0 + a.seeds)
+        series, t_iter, wall = ref_harness.run_ensemble(seeds, days=days, processes=a.processes,
+                                                        area=area, scenario=scenario)
+        out = os.path.join(HERE, 'ref_ensemble_%s.npz' % name)
+        np.savez_compressed(
+            out, mean=series.mean(axis=0), std=series.std(axis=0, ddof=1), n=len(seeds),
+            names=np.array(ref_harness.series_names()), seeds=seeds,
+            iterate_seconds=t_iter, area=area, scenario=str(scenario), days=days)
+        print('%s: %d seeds in %.0f s (mean iterate %.1f s/seed) -> %s' % (
+            name, len(seeds), time.time() - t0, t_iter.mean(), out), flush=True)
+
+
+if __name__ == '__main__':
+    main()

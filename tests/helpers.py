@@ -1,0 +1,85 @@
+"""Shared test helpers: bind the CPU oracle / the CUDA library through the same ctypes wrapper."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from reina_b200 import _abi, inputs, model  # noqa: E402
+
+ORACLE_PATH = os.path.join(ROOT, 'oracle', 'libreina_oracle.so')
+_oracle = None
+
+# order of oracle/ref_harness.series_names()
+POP_SERIES = ['susceptible', 'vaccinated', 'infected', 'all_infected', 'detected', 'all_detected',
+              'in_icu', 'cum_icu', 'in_ward', 'dead', 'recovered', 'non_hospital_deaths', 'new_infections']
+SCALAR_SERIES = ['available_icu_units', 'available_hospital_beds', 'total_icu_units', 'r',
+                 'exposed_per_day', 'ct_cases_per_day', 'mobility_limitation']
+PLACES = ['home', 'work', 'school', 'transport', 'leisure', 'other']
+
+
+def oracle_library():
+    global _oracle
+    if _oracle is None:
+        subprocess.run(['make', '-s', '-C', os.path.join(ROOT, 'oracle')], check=True)
+        _oracle = _abi.Library(ORACLE_PATH, 'ro_')
+    return _oracle
+
+
+def cuda_library():
+    return _abi.cuda_library()
+
+
+def make_context(lib, area='HUS', scenario=None, seed=0, n_replicas=1, variables=None,
+                 age_count_override=None, interventions=None, max_days=200, **kw):
+    v = variables or inputs.default_variables()
+    args = inputs.build_context_args(v, area=area, age_count_override=age_count_override)
+    args['random_seed'] = seed
+    ctx = model.Context(n_replicas=n_replicas, max_days=max_days, _library=lib, **args, **kw)
+    ivs = interventions if interventions is not None else inputs.active_interventions(v, scenario)
+    for iv in ivs:
+        ctx.add_intervention(iv)
+    return ctx
+
+
+def small_population(total, area='HUS'):
+    return inputs.synthetic_age_counts(total, area)
+
+
+def series_matrix(ctx, days=None):
+    """[replica, day, series] float64 in the order of oracle/ref_harness.series_names()."""
+    rows = ctx.series(0, days)
+    R, D, _ = rows.shape
+    G = len(ctx.age_group_labels)
+    nA = len(_abi.ATTRS)
+    out = np.zeros((R, D, len(POP_SERIES) + len(SCALAR_SERIES) + len(PLACES) + len(ctx.variant_names)))
+    sc = rows[:, :, nA * G:].astype(np.float64)
+    S = {name: sc[:, :, i] for i, name in enumerate(_abi.SCALARS)}
+    k = 0
+    for a in POP_SERIES:
+        i = _abi.ATTRS.index(a)
+        out[:, :, k] = rows[:, :, i * G:(i + 1) * G].sum(axis=2)
+        k += 1
+    with np.errstate(divide='ignore', invalid='ignore'):
+        r = np.where(S['total_infectors'] > 5, S['total_infections'] / np.maximum(S['total_infectors'], 1), 0.0)
+    mob = np.vectorize(lambda ep: ctx._epoch_mobility.get(int(ep), 0.0))(S['table_epoch'])
+    for name in SCALAR_SERIES:
+        out[:, :, k] = r if name == 'r' else (mob if name == 'mobility_limitation' else S[name])
+        k += 1
+    place_idx = {'home': 0, 'work': 1, 'school': 2, 'transport': 3, 'leisure': 4, 'other': 5}
+    for p in PLACES:
+        out[:, :, k] = sc[:, :, _abi.RB_S_CONTACTS0 + place_idx[p]]
+        k += 1
+    for i in range(len(ctx.variant_names)):
+        out[:, :, k] = sc[:, :, _abi.RB_S_VARIANT0 + i]
+        k += 1
+    return out
+
+
+def series_names(variant_names=('wild-type', 'b1.1.7')):
+    return (POP_SERIES + SCALAR_SERIES + ['exposures_%s' % p for p in PLACES]
+            + ['infected_by_variant_%s' % v for v in variant_names])
