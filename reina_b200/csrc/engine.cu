@@ -1,0 +1,1200 @@
+// reina_b200 engine: the per-day agent loop of Reina (cythonsim/main.pyx Context.iterate and everything it
+// calls) as hand-written CUDA for sm_100a, behind the C-ABI of include/reina_b200.h.
+//
+// Data layout (per replica, structure of arrays in HBM, agents stored AGE-SORTED so that age is implied by
+// position and a contact target is age_start[band] + u32 % band_size with no indirection):
+//   hot[N]      u32  packed word streamed by the daily sweep: state 3b | severity 3b | detected | queued |
+//                    variant 2b | fresh | included_in_totals | has_list | vaccinated | days_left 8b | day_of_illness 5b
+//   cold[N]     u32  other_people_infected 16b | ward_days 8b | icu_days 8b      (touched by infected agents only)
+//   infector[N], first_child[N], next_sib[N], inf_key[N]   infection tree for contact tracing
+//   vacc_day[N] i16, winner[N] u64 (atomicMin conflict slots, all-ones when idle)
+// Per day (reference order, main.pyx:1994-2016):
+//   k_pre     1 CTA / replica   stats row, intervention deltas, imports, test queue drain + contact tracing,
+//                               vaccination, sweep start draw
+//   k_sweep   grid              Context._iterate_people / person_advance over the packed words; emits contact
+//                               work items, capacity events and test-queue entries tagged with sweep position
+//   k_expose  grid              one thread per sampled contact: row search, target gather, transmission draw,
+//                               atomicMin(winner[target], sweep position of infector | slot)
+//   k_resolve grid              winners become infected (severity, incubation draw, infection tree)
+//   k_post    1 CTA / replica   beds/ICU first-come-first-served = sort by sweep position + max-plus scan
+// Every order-dependent step of the sequential reference is resolved through the agent's sweep position, so the
+// result is bit-identical to the sequential CPU oracle and independent of scheduling.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/reina_b200.h"
+#include "rng.cuh"
+
+#define MAX_INFECTEES 64   // main.pyx:128
+#define MAX_CONTACTS 128   // main.pyx:129
+
+// ---------------------------------------------------------------- packed hot word
+#define H_STATE(h) ((h) & 7u)
+#define H_SEV(h) (((h) >> 3) & 7u)
+#define H_DET (1u << 6)
+#define H_QUEUED (1u << 7)
+#define H_VAR(h) (((h) >> 8) & 3u)
+#define H_FRESH (1u << 10)
+#define H_INCL (1u << 11)
+#define H_LIST (1u << 12)
+#define H_VACC (1u << 13)
+#define H_DL(h) (((h) >> 14) & 255u)
+#define H_DOI(h) (((h) >> 22) & 31u)
+#define H_SET_STATE(h, s) (((h) & ~7u) | (uint32_t)(s))
+#define H_SET_DL(h, d) (((h) & ~(255u << 14)) | ((uint32_t)(d) << 14))
+#define H_SET_DOI(h, d) (((h) & ~(31u << 22)) | ((uint32_t)(d) << 22))
+
+#define KEY_IDLE 0xFFFFFFFFFFFFFFFFull
+#define QKEY_SWEEP (1ull << 62)
+#define CT_DEAD (1ull << 61)
+#define CT_DECIDED (1ull << 60)
+#define CT_KEYMASK ((1ull << 60) - 1ull)
+
+enum { EV_HOSP_CLAIM = 0, EV_WARD_RELEASE = 1, EV_TO_ICU = 2, EV_ICU_RELEASE = 3 };
+
+#define SORT_SMEM 2048
+#define PRE_THREADS 1024
+#define NEG_INF (-(1 << 29))
+
+struct DevTable {
+    int32_t n_rows[RB_MAX_AGES];
+    float nr_contacts[RB_MAX_AGES];
+    double cum_p[RB_MAX_AGES][RB_MAX_ROWS];
+    int32_t start[RB_MAX_AGES][RB_MAX_ROWS];
+    int32_t size[RB_MAX_AGES][RB_MAX_ROWS];
+    float mask_p[RB_MAX_AGES][RB_MAX_ROWS];
+    uint8_t place[RB_MAX_AGES][RB_MAX_ROWS];
+};
+
+struct Attempt { uint32_t cand, parent; unsigned long long key; };
+
+struct RepCtr {
+    int32_t counts[RB_N_ATTRS][RB_MAX_AGES];
+    int32_t daily_contacts[RB_N_PLACES];
+    int32_t by_variant[RB_MAX_VARIANTS];
+    int32_t beds, icu, avail_beds, avail_icu;
+    int32_t total_infectors, total_infections, exposed_per_day, ct_cases;
+    int32_t problem, epoch, testing_mode, day;
+    float p_detected_anyway, p_successful_tracing;
+    uint32_t seed, start;
+    uint32_t fkey[4];
+    uint32_t n_items, n_succ, n_events, n_queue, n_newq, qsel;
+    uint32_t n_l0, n_l1, n_edges, pad0;
+    int32_t vacc_cursor[RB_MAX_VACC];
+    int32_t pad[8];
+};
+
+struct Eng {
+    int32_t N, Npad, n_ages, n_groups, n_variants, R, max_days, row_len, n_import_classes, fhalf;
+    uint32_t cap_items, cap_succ, cap_events, cap_queue;
+    uint32_t *hot, *cold, *inf_key;
+    int32_t *infector, *first_child, *next_sib;
+    int16_t *vacc_day;
+    unsigned long long *winner;
+    uint2 *items;
+    Attempt *succ;
+    unsigned long long *ev_key; int32_t *ev_agent;
+    unsigned long long *q_key; int32_t *q_agent;   // [R][2][cap_queue]
+    RepCtr *ctr;
+    int32_t *stats;                                // [R][max_days+1][row_len]
+    const rb_day_params *sched;
+    DevTable *const *tables;
+    const rb_variant *variants;
+    const int32_t *age_start;                      // [n_ages+1]
+    const int32_t *group_of_age;
+    const int32_t *import_lo, *import_hi; const float *import_cum;
+};
+
+// ---------------------------------------------------------------- small device helpers
+__device__ __forceinline__ int age_of(const Eng &G, int32_t a) {
+    int lo = 0, hi = G.n_ages;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(&G.age_start[mid]) <= a) lo = mid; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ uint32_t sweep_pos(const Eng &G, const RepCtr *c, uint32_t a) {
+    uint32_t s = feistel(a, (uint32_t)G.N, G.fhalf, c->fkey[0], c->fkey[1], c->fkey[2], c->fkey[3]);
+    return s >= c->start ? s - c->start : s + (uint32_t)G.N - c->start;
+}
+__device__ __forceinline__ void count_add(RepCtr *c, int attr, int age, int d) { atomicAdd(&c->counts[attr][age], d); }
+__device__ __forceinline__ void set_problem(RepCtr *c, int p) { atomicCAS(&c->problem, 0, p); }
+
+// Disease.get_symptom_severity, main.pyx:1042-1091 (every FATAL case dies outside hospital, SURVEY 8a note 2)
+__device__ __forceinline__ int symptom_severity(const rb_variant *v, int age, float val, bool vacc_eff) {
+    float vmod = 1.0f;
+    if (vacc_eff) vmod = vmod * 0.1f;
+    float syc = v->tab[RB_T_SYMPTOMATIC][age];
+    if (val >= syc) return RB_ASYMPTOMATIC;
+    syc = syc * vmod;
+    float dohc = v->tab[RB_T_DEATH_OUTSIDE_HOSPITAL][age];
+    if (dohc != 0.0f) {
+        if (val < dohc * syc) return RB_FATAL;
+        val = (val - dohc) / (1.0f - dohc);
+    }
+    float sc = v->tab[RB_T_SEVERE][age], cc = v->tab[RB_T_CRITICAL][age], fc = v->tab[RB_T_FATAL][age];
+    if (val < ((fc * cc) * sc) * syc) return RB_FATAL;
+    if (val < (cc * sc) * syc) return RB_CRITICAL;
+    if (val < sc * syc) return RB_SEVERE;
+    return RB_MILD;
+}
+
+// person_infect, main.pyx:209-235 + Population.infect :1576-1582.  `src_h` = packed word of the infector
+// (ignored when src < 0).  Severity and incubation use wild-type parameters (variant_idx is still 0 there).
+__device__ void device_infect(const Eng &G, int r, RepCtr *c, int32_t t, int32_t src, uint32_t src_h, int variant,
+                              int slot, bool fresh) {
+    size_t base = (size_t)r * G.Npad;
+    int day = c->day;
+    int age = age_of(G, t);
+    const rb_variant *v0 = &G.variants[0];
+    uint32_t h = G.hot[base + t];
+    int vd = G.vacc_day[base + t];
+    bool vacc_eff = vd >= 0 && (day - vd) > 14;
+    u32x4 x = philox(c->seed, (uint32_t)t, (uint32_t)day, PU_SEVERITY, 0);
+    int sev = symptom_severity(v0, age, u01f(x.x), vacc_eff);
+    int dl = clamp255(round_to_int(gamma_f(c->seed, (uint32_t)t, (uint32_t)day, PU_INCUB, v0->incubation_kappa, v0->incubation_theta)));
+    if (src >= 0) {
+        variant = (int)H_VAR(src_h);
+        G.infector[base + t] = src;
+        uint32_t old = atomicAdd(&G.cold[base + src], 1u) & 0xffffu;
+        if ((src_h & H_LIST) && old >= MAX_INFECTEES) set_problem(c, RB_TOO_MANY_INFECTEES);
+        G.inf_key[base + t] = ((uint32_t)day << 8) | (uint32_t)slot;
+        G.next_sib[base + t] = atomicExch(&G.first_child[base + src], t);
+    }
+    uint32_t nh = (h & H_VACC) | RB_INCUBATION | ((uint32_t)sev << 3) | ((uint32_t)variant << 8) | ((uint32_t)dl << 14);
+    if (fresh) nh |= H_FRESH;
+    if (c->testing_mode == RB_ALL_WITH_SYMPTOMS_CT) nh |= H_LIST;
+    G.hot[base + t] = nh;
+    count_add(c, RB_A_SUSCEPTIBLE, age, -1);
+    count_add(c, RB_A_INFECTED, age, 1);
+    count_add(c, RB_A_ALL_INFECTED, age, 1);
+    count_add(c, RB_A_NEW_INFECTIONS, age, 1);
+    atomicAdd(&c->by_variant[variant], 1);
+}
+
+// ---------------------------------------------------------------- block-wide helpers (single CTA)
+// Bitonic sort of (key, val) pairs, ascending by key; n <= SORT_SMEM sorts in shared memory, larger lists in
+// place in global memory (capacity must be a power of two >= n; the tail is padded with KEY_IDLE).
+__device__ void block_sort_pairs(unsigned long long *keys, int32_t *vals, uint32_t n, uint32_t cap,
+                                 unsigned long long *sk, int32_t *sv) {
+    if (n <= 1) return;
+    uint32_t m = 1; while (m < n) m <<= 1;
+    if (m <= SORT_SMEM) {
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) { sk[i] = i < n ? keys[i] : KEY_IDLE; sv[i] = i < n ? vals[i] : -1; }
+        __syncthreads();
+        for (uint32_t k = 2; k <= m; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                    uint32_t l = i ^ j;
+                    if (l > i) {
+                        bool up = (i & k) == 0;
+                        unsigned long long a = sk[i], b = sk[l];
+                        if ((a > b) == up) { sk[i] = b; sk[l] = a; int32_t t = sv[i]; sv[i] = sv[l]; sv[l] = t; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { keys[i] = sk[i]; vals[i] = sv[i]; }
+        __syncthreads();
+        return;
+    }
+    if (m > cap) m = cap;
+    for (uint32_t i = n + threadIdx.x; i < m; i += blockDim.x) { keys[i] = KEY_IDLE; vals[i] = -1; }
+    __syncthreads();
+    for (uint32_t k = 2; k <= m; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                uint32_t l = i ^ j;
+                if (l > i) {
+                    bool up = (i & k) == 0;
+                    unsigned long long a = keys[i], b = keys[l];
+                    if ((a > b) == up) { keys[i] = b; keys[l] = a; int32_t t = vals[i]; vals[i] = vals[l]; vals[l] = t; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// inclusive block scan of one int per thread (blockDim.x <= 1024); returns inclusive prefix, *total = block sum
+__device__ int block_scan_incl(int v, int *total, int *warp_sums) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) warp_sums[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        warp_sums[lane] = s;
+    }
+    __syncthreads();
+    int prefix = w > 0 ? warp_sums[w - 1] : 0;
+    *total = warp_sums[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    return v + prefix;
+}
+
+// Context.generate_state, main.pyx:1813-1857: fold per-age counters into age groups + scalars.
+__device__ void write_stats_row(const Eng &G, int r, RepCtr *c, int32_t *srow /* shared, >= row_len */) {
+    int day = c->day;
+    for (int i = threadIdx.x; i < G.row_len; i += blockDim.x) srow[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < RB_N_ATTRS * G.n_ages; i += blockDim.x) {
+        int a = i / G.n_ages, age = i - a * G.n_ages;
+        int v = c->counts[a][age];
+        if (v) atomicAdd(&srow[a * G.n_groups + G.group_of_age[age]], v);
+    }
+    if (threadIdx.x == 0) {
+        int32_t *s = srow + RB_N_ATTRS * G.n_groups;
+        s[RB_S_AVAILABLE_ICU] = c->avail_icu; s[RB_S_AVAILABLE_BEDS] = c->avail_beds;
+        s[RB_S_TOTAL_ICU] = c->icu; s[RB_S_TOTAL_BEDS] = c->beds;
+        s[RB_S_TOTAL_INFECTIONS] = c->total_infections; s[RB_S_TOTAL_INFECTORS] = c->total_infectors;
+        s[RB_S_EXPOSED_PER_DAY] = c->exposed_per_day; s[RB_S_CT_CASES_PER_DAY] = c->ct_cases;
+        s[RB_S_TABLE_EPOCH] = c->epoch; s[RB_S_DAY] = day;
+        for (int i = 0; i < RB_N_PLACES; i++) s[RB_S_CONTACTS0 + i] = c->daily_contacts[i];
+        for (int i = 0; i < RB_MAX_VARIANTS; i++) s[RB_S_VARIANT0 + i] = c->by_variant[i];
+    }
+    __syncthreads();
+    int32_t *row = G.stats + ((size_t)r * (G.max_days + 1) + day) * G.row_len;
+    for (int i = threadIdx.x; i < G.row_len; i += blockDim.x) row[i] = srow[i];
+    __syncthreads();
+}
+
+// Population.infect_people + get_import_infection_person, main.pyx:1632-1665 (sequential: a person picked by an
+// earlier import of the same day is no longer SUSCEPTIBLE for a later one).  Run by one thread.
+__device__ void import_infections(const Eng &G, int r, RepCtr *c, int count, int variant, int *ordinal) {
+    size_t base = (size_t)r * G.Npad;
+    for (int i = 0; i < count; i++) {
+        uint32_t ord = (uint32_t)(*ordinal)++;
+        int32_t found = -1;
+        for (uint32_t t = 0; t < 10; t++) {
+            u32x4 x = philox(c->seed, ord, (uint32_t)c->day, PU_IMPORT | (t << 8), 0);
+            float p = u01f(x.x);
+            int k = G.n_import_classes - 1;
+            for (int j = 0; j < G.n_import_classes; j++) if (p <= G.import_cum[j]) { k = j; break; }
+            int32_t s = G.age_start[G.import_lo[k]], en = G.age_start[G.import_hi[k] + 1];
+            int32_t pi = s + (int32_t)(x.y % (uint32_t)(en - s));
+            if (H_STATE(G.hot[base + pi]) == RB_SUSCEPTIBLE) { found = pi; break; }
+        }
+        if (found >= 0) device_infect(G, r, c, found, -1, 0u, variant, 0, true);
+    }
+}
+
+// Candidates a tracer reaches (perform_contact_tracing, main.pyx:495-512): slot 0 = its infector, slots 1.. =
+// its infectees in infection order (only while the tracer is infected and owns a list, :227-233, :305-307).
+__device__ int trace_candidates(const Eng &G, size_t base, int32_t x, uint32_t hx, int32_t *cand /*[65]*/, int *first_slot) {
+    int n = 0;
+    int32_t inf = G.infector[base + x];
+    *first_slot = 1;
+    if (inf >= 0) { cand[0] = inf; n = 1; *first_slot = 0; }
+    uint32_t st = H_STATE(hx);
+    if ((hx & H_LIST) && st >= RB_INCUBATION && st <= RB_IN_ICU) {
+        uint32_t keys[MAX_INFECTEES];
+        int m = 0;
+        int32_t *kids = cand + 1;
+        for (int32_t ch = G.first_child[base + x]; ch >= 0 && m < MAX_INFECTEES; ch = G.next_sib[base + ch]) {
+            uint32_t k = G.inf_key[base + ch];
+            int j = m++;
+            while (j > 0 && keys[j - 1] > k) { keys[j] = keys[j - 1]; kids[j] = kids[j - 1]; j--; }
+            keys[j] = k; kids[j] = ch;
+        }
+        n = 1 + m;
+    } else if (inf < 0) n = 0;
+    return n;   // valid slots: [*first_slot, n)
+}
+
+__device__ __forceinline__ bool trace_eligible(uint32_t h) {   // queue_for_testing guards, main.pyx:476-477
+    return H_STATE(h) != RB_DEAD && !(h & (H_DET | H_QUEUED));
+}
+
+// ---------------------------------------------------------------- k_pre
+__global__ void __launch_bounds__(PRE_THREADS) k_pre(Eng G) {
+    __shared__ unsigned long long sk[SORT_SMEM];
+    __shared__ int32_t sv[SORT_SMEM];
+    __shared__ int32_t srow[RB_N_ATTRS * 16 + RB_N_SCALARS];
+    __shared__ int warp_sums[32];
+    __shared__ int sh_i[4];
+    const int r = blockIdx.x;
+    RepCtr *c = &G.ctr[r];
+    const size_t base = (size_t)r * G.Npad;
+    const int day = c->day;
+    const rb_day_params *dp = &G.sched[day];
+    const int tid = threadIdx.x;
+
+    write_stats_row(G, r, c, srow);
+
+    // apply_intervention effects dated today (main.pyx:1880-1960), then Population.init_day (:1687-1699)
+    if (tid == 0) {
+        c->testing_mode = dp->testing_mode;
+        c->p_detected_anyway = dp->p_detected_anyway;
+        c->p_successful_tracing = dp->p_successful_tracing;
+        c->beds += dp->beds_delta; c->avail_beds += dp->beds_delta;
+        c->icu += dp->icu_delta; c->avail_icu += dp->icu_delta;
+        int ordinal = 0;
+        for (int i = 0; i < dp->n_imports; i++) import_infections(G, r, c, dp->import_amount[i], dp->import_variant[i], &ordinal);
+        sh_i[0] = ordinal;
+    }
+    __syncthreads();
+    for (int i = tid; i < G.n_ages; i += blockDim.x) { c->counts[RB_A_NEW_INFECTIONS][i] = 0; c->counts[RB_A_DETECTED][i] = 0; }
+    if (tid < RB_N_PLACES) c->daily_contacts[tid] = 0;
+    if (tid < RB_MAX_VARIANTS) c->by_variant[tid] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        c->epoch = dp->table_epoch;
+        int ordinal = sh_i[0];
+        for (int v = 0; v < G.n_variants; v++) if (dp->trickle[v]) import_infections(G, r, c, dp->trickle[v], v, &ordinal);
+        c->total_infectors = 0; c->total_infections = 0; c->exposed_per_day = 0;
+    }
+    __syncthreads();
+
+    // HealthcareSystem.iterate (main.pyx:514-558): drain yesterday's queue
+    const uint32_t cur = c->qsel, nxt = cur ^ 1u;
+    unsigned long long *qk = G.q_key + ((size_t)r * 2 + cur) * G.cap_queue;
+    int32_t *qa = G.q_agent + ((size_t)r * 2 + cur) * G.cap_queue;
+    unsigned long long *nk = G.q_key + ((size_t)r * 2 + nxt) * G.cap_queue;
+    int32_t *na = G.q_agent + ((size_t)r * 2 + nxt) * G.cap_queue;
+    const uint32_t nq = c->n_queue;
+    const bool ct = c->testing_mode == RB_ALL_WITH_SYMPTOMS_CT;
+    if (tid == 0) { c->ct_cases = (int32_t)nq; c->n_newq = 0; c->n_l0 = 0; c->n_l1 = 0; c->n_edges = 0; }
+    if (ct) block_sort_pairs(qk, qa, nq, G.cap_queue, sk, sv);   // queue order only matters for tracing
+    __syncthreads();
+    for (uint32_t i = tid; i < nq; i += blockDim.x) {
+        int32_t a = qa[i];
+        uint32_t h = G.hot[base + a];
+        if (h & H_DET) set_problem(c, RB_WRONG_STATE);   // person_detect, main.pyx:294-298
+        G.hot[base + a] = (h & ~H_QUEUED) | H_DET;
+        int age = age_of(G, a);
+        count_add(c, RB_A_DETECTED, age, 1); count_add(c, RB_A_ALL_DETECTED, age, 1);
+    }
+    __syncthreads();
+
+    if (ct && nq > 0) {
+        // Depth-first contact tracing resolved in parallel.  Attempt key = (queue rank, level-0 slot, level-1 slot);
+        // an attempt queues its candidate iff it is the smallest-key LIVE attempt on it that EXISTS; a level-1
+        // attempt exists iff its tracer was itself queued by a level-0 attempt (main.pyx:498-499, 505-512).
+        unsigned long long *win = G.winner + base;
+        Attempt *l0 = G.succ + (size_t)r * G.cap_succ;
+        Attempt *l1 = (Attempt *)(G.items + (size_t)r * G.cap_items);
+        const uint32_t cap_l1 = G.cap_items / 2;
+        const float ptr = c->p_successful_tracing;
+        for (uint32_t i = tid; i < nq; i += blockDim.x) {
+            int32_t x = qa[i];
+            int32_t cand[MAX_INFECTEES + 1]; int first;
+            int n = trace_candidates(G, base, x, G.hot[base + x], cand, &first);
+            for (int a = first; a < n; a++) {
+                int32_t cc = cand[a];
+                if (!trace_eligible(G.hot[base + cc])) continue;
+                u32x4 rx = philox(c->seed, (uint32_t)x, (uint32_t)day, PU_TRACE, (uint32_t)cc);
+                if (!chance(u01d(rx.x, rx.y), ptr)) continue;
+                unsigned long long key = ((unsigned long long)i << 14) | ((unsigned long long)a << 7);
+                uint32_t idx = atomicAdd(&c->n_l0, 1u);
+                if (idx < G.cap_succ) { l0[idx].cand = (uint32_t)cc; l0[idx].parent = (uint32_t)x; l0[idx].key = key; atomicMin(&win[cc], key); }
+                else set_problem(c, RB_OTHER_FAILURE);
+            }
+        }
+        __syncthreads();
+        uint32_t n0 = min(c->n_l0, G.cap_succ);
+        for (uint32_t j = tid; j < n0; j += blockDim.x) {
+            Attempt at = l0[j];
+            if (win[at.cand] != at.key) continue;
+            int32_t x = (int32_t)at.cand;
+            int32_t cand[MAX_INFECTEES + 1]; int first;
+            int n = trace_candidates(G, base, x, G.hot[base + x], cand, &first);
+            for (int b = first; b < n; b++) {
+                int32_t cc = cand[b];
+                if (!trace_eligible(G.hot[base + cc])) continue;
+                u32x4 rx = philox(c->seed, (uint32_t)x, (uint32_t)day, PU_TRACE, (uint32_t)cc);
+                if (!chance(u01d(rx.x, rx.y), ptr)) continue;
+                uint32_t idx = atomicAdd(&c->n_l1, 1u);
+                if (idx < cap_l1) { l1[idx].cand = (uint32_t)cc; l1[idx].parent = (uint32_t)x; l1[idx].key = at.key | (unsigned long long)(b + 1); }
+                else set_problem(c, RB_OTHER_FAILURE);
+            }
+        }
+        __syncthreads();
+        uint32_t n1 = min(c->n_l1, cap_l1);
+        // kill edges: a level-1 attempt that precedes the level-0 winner of the same candidate
+        uint32_t *esrc = (uint32_t *)(G.ev_key + (size_t)r * G.cap_events);
+        uint32_t *edst = (uint32_t *)(G.ev_agent + (size_t)r * G.cap_events);
+        const uint32_t cap_e = G.cap_events;
+        for (uint32_t k = tid; k < n1; k += blockDim.x) {
+            unsigned long long w = win[l1[k].cand];
+            if (w != KEY_IDLE && l1[k].key < w) {
+                uint32_t idx = atomicAdd(&c->n_edges, 1u);
+                if (idx < cap_e) { esrc[idx] = l1[k].parent; edst[idx] = l1[k].cand; } else set_problem(c, RB_OTHER_FAILURE);
+            }
+        }
+        __syncthreads();
+        uint32_t ne = min(c->n_edges, cap_e);
+        if (ne > 0 && tid == 0) {
+            // decide candidates in increasing order of their level-0 key: a candidate loses its tracing rights iff
+            // some level-1 attempt from a tracer that kept its rights precedes its own level-0 attempt
+            for (;;) {
+                unsigned long long best = KEY_IDLE; uint32_t bd = 0;
+                for (uint32_t k = 0; k < ne; k++) {
+                    unsigned long long w = win[edst[k]];
+                    if (!(w & CT_DECIDED) && (w & CT_KEYMASK) < best) { best = w & CT_KEYMASK; bd = edst[k]; }
+                }
+                if (best == KEY_IDLE) break;
+                bool dead = false;
+                for (uint32_t k = 0; k < ne; k++) if (edst[k] == bd && !(win[esrc[k]] & CT_DEAD)) { dead = true; break; }
+                win[bd] = best | CT_DECIDED | (dead ? CT_DEAD : 0ull);
+            }
+            for (uint32_t k = 0; k < ne; k++) {
+                unsigned long long w = win[edst[k]];
+                if (w == KEY_IDLE) continue;
+                win[edst[k]] = (w & CT_DEAD) ? KEY_IDLE : (w & CT_KEYMASK);
+            }
+        }
+        __syncthreads();
+        for (uint32_t k = tid; k < n1; k += blockDim.x) {
+            Attempt e = l1[k];
+            if (win[e.parent] == (e.key & ~127ull)) atomicMin(&win[e.cand], e.key);
+        }
+        __syncthreads();
+        for (uint32_t j = tid; j < n0 + n1; j += blockDim.x) {
+            Attempt e = j < n0 ? l0[j] : l1[j - n0];
+            if (win[e.cand] != e.key) continue;
+            if (j >= n0 && win[e.parent] != (e.key & ~127ull)) continue;
+            uint32_t idx = atomicAdd(&c->n_newq, 1u);
+            if (idx < G.cap_queue) { nk[idx] = e.key; na[idx] = (int32_t)e.cand; } else set_problem(c, RB_OTHER_FAILURE);
+            G.hot[base + e.cand] |= H_QUEUED;
+        }
+        __syncthreads();
+        for (uint32_t j = tid; j < n0 + n1; j += blockDim.x) { Attempt e = j < n0 ? l0[j] : l1[j - n0]; win[e.cand] = KEY_IDLE; }
+        __syncthreads();
+    }
+
+    // vaccinate_people (main.pyx:560-583): top-down walk of the age-sorted range; eligibility only ever turns
+    // off (dead / vaccinated / detected), so a per-programme cursor below which the walk resumes is exact.
+    for (int p = 0; p < dp->n_vacc; p++) {
+        int nr = dp->vacc_nr[p];
+        if (!nr) continue;
+        int slot = dp->vacc_slot[p];
+        int32_t s = G.age_start[dp->vacc_min_age[p]], en = G.age_start[dp->vacc_max_age[p] + 1];
+        if (nr > en - s) nr = en - s;
+        int32_t pos = c->vacc_cursor[slot];                 // -2 = programme not started yet
+        if (pos == -2 || pos > en - 1) pos = en - 1;
+        int done = 0;
+        __syncthreads();
+        while (done < nr && pos >= s) {
+            int32_t idx = pos - tid;
+            uint32_t h = 0; bool el = false;
+            if (idx >= s) { h = G.hot[base + idx]; el = H_STATE(h) != RB_DEAD && !(h & (H_VACC | H_DET)); }
+            int total;
+            int rank = block_scan_incl(el ? 1 : 0, &total, warp_sums);
+            int want = nr - done;
+            if (el && rank <= want) {
+                G.hot[base + idx] = h | H_VACC;
+                G.vacc_day[base + idx] = (int16_t)day;
+                count_add(c, RB_A_VACCINATED, age_of(G, idx), 1);
+                if (rank == want) sh_i[1] = idx - 1;      // walk stops right below the last person vaccinated
+            }
+            __syncthreads();
+            if (total >= want) { done = nr; pos = sh_i[1]; }
+            else { done += total; pos -= (int32_t)blockDim.x; }
+            __syncthreads();
+        }
+        if (tid == 0) c->vacc_cursor[slot] = pos < s - 1 ? s - 1 : pos;
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+        u32x4 x = philox(c->seed, 0u, (uint32_t)day, PU_START, 0);     // _iterate_people, main.pyx:1988
+        c->start = x.x % (uint32_t)G.N;
+        c->n_items = 0; c->n_succ = 0; c->n_events = 0;
+    }
+}
+
+// ---------------------------------------------------------------- k_sweep
+struct SweepOut { uint32_t n; uint32_t desc; };
+
+// _process_person + person_advance (main.pyx:1968-1979, 395-438) for one agent word.  Returns the number of
+// contacts to sample (person_expose_others :247-281 runs in k_expose) and whether the word changed.
+__device__ __forceinline__ uint32_t advance_agent(const Eng &G, int r, RepCtr *c, const DevTable *tb, int32_t a, uint32_t &h, bool &dirty, uint32_t &desc) {
+    const size_t base = (size_t)r * G.Npad;
+    uint32_t st = H_STATE(h);
+    if (st >= RB_RECOVERED) {
+        if (!(h & H_INCL)) {           // R bookkeeping, main.pyx:1969-1972
+            atomicAdd(&c->total_infectors, 1);
+            atomicAdd(&c->total_infections, (int)(G.cold[base + a] & 0xffffu));
+            h |= H_INCL; dirty = true;
+        }
+        return 0;
+    }
+    if (st == RB_SUSCEPTIBLE) return 0;
+    if (h & H_FRESH) { h &= ~H_FRESH; dirty = true; return 0; }   // infected today before the sweep, main.pyx:402-403
+    dirty = true;
+    const int day = c->day;
+    const int age = age_of(G, a);
+    const uint32_t sev = H_SEV(h), var = H_VAR(h);
+    const rb_variant *v = &G.variants[var];
+    uint32_t n = 0;
+    if (st == RB_INCUBATION || st == RB_ILLNESS) {
+        // get_exposed_people / get_nr_contacts, main.pyx:936-955, 1308-1320
+        int dayidx = st == RB_INCUBATION ? -(int)H_DL(h) : (int)H_DOI(h);
+        if (!(h & H_DET) && dayidx >= -10 && dayidx <= 10 && v->iot[dayidx + 10] != 0.0f) {
+            float factor = 1.0f; int limit = 100;
+            if (st == RB_ILLNESS && sev != RB_ASYMPTOMATIC) { factor = 0.5f; limit = 5; }
+            float f = lognormal_half(c->seed, (uint32_t)a, (uint32_t)day, PU_NCONTACT) * tb->nr_contacts[age];
+            f = f * factor;
+            if (f < 1.0f) f = 1.0f;
+            int k = (int)f - 1;
+            if (k > limit) k = limit;
+            if (k > MAX_CONTACTS) { set_problem(c, RB_TOO_MANY_CONTACTS); k = 0; }
+            n = (uint32_t)k;
+            desc = ((uint32_t)age << 7) | ((uint32_t)(dayidx + 10) << 14) | ((sev == RB_ASYMPTOMATIC ? 1u : 0u) << 19) | (var << 20);
+        }
+    }
+    uint32_t dl = H_DL(h);
+    if (st == RB_INCUBATION) {
+        if (dl > 0) dl--;
+        if (dl == 0) {
+            // person_become_ill, main.pyx:284-291; durations :989-1039 fixed from the one onset-to-removed draw
+            float T = (sev == RB_FATAL)
+                ? gamma_f(c->seed, (uint32_t)a, (uint32_t)day, PU_ONSET, v->onset_death_kappa, v->onset_death_theta)
+                : gamma_f(c->seed, (uint32_t)a, (uint32_t)day, PU_ONSET, v->onset_recovery_kappa, v->onset_recovery_theta);
+            float f = T;
+            if (sev != RB_ASYMPTOMATIC && sev != RB_MILD) f = f * v->ratio_before_hospitalisation;
+            dl = (uint32_t)clamp255(round_to_int(f));
+            float w = 0.0f, u = 0.0f;
+            if (sev == RB_SEVERE) w = T * (1.0f - v->ratio_before_hospitalisation);
+            else if (sev == RB_CRITICAL || sev == RB_FATAL) {
+                w = T * v->ratio_in_ward;
+                u = ((1.0f - v->ratio_in_ward) - v->ratio_before_hospitalisation) * T;
+            }
+            uint32_t wd = (uint32_t)clamp255(round_to_int(w)), ud = (uint32_t)clamp255(round_to_int(u));
+            atomicOr(&G.cold[base + a], (wd << 16) | (ud << 24));
+            h = H_SET_STATE(h, RB_ILLNESS);
+            if (sev != RB_ASYMPTOMATIC && !(h & H_DET)) {
+                // seek_testing, main.pyx:595-615
+                bool q = false;
+                int mode = c->testing_mode;
+                if (mode == RB_ALL_WITH_SYMPTOMS || mode == RB_ALL_WITH_SYMPTOMS_CT) q = true;
+                else if (mode == RB_ONLY_SEVERE_SYMPTOMS) {
+                    if (sev >= RB_SEVERE) q = true;
+                    else {
+                        u32x4 x = philox(c->seed, (uint32_t)a, (uint32_t)day, PU_SEEK, 0);
+                        q = chance(u01d(x.x, x.y), c->p_detected_anyway);
+                    }
+                }
+                if (q && !(h & H_QUEUED)) {     // queue_for_testing guards (not DEAD / detected / queued), main.pyx:476
+                    h |= H_QUEUED;
+                    uint32_t idx = atomicAdd(&c->n_newq, 1u);
+                    if (idx < G.cap_queue) {
+                        size_t qb = ((size_t)r * 2 + (c->qsel ^ 1u)) * G.cap_queue;
+                        G.q_key[qb + idx] = QKEY_SWEEP | sweep_pos(G, c, (uint32_t)a);
+                        G.q_agent[qb + idx] = a;
+                    } else set_problem(c, RB_OTHER_FAILURE);
+                }
+            }
+        }
+        h = H_SET_DL(h, dl);
+    } else if (st == RB_ILLNESS) {
+        uint32_t doi = H_DOI(h);
+        if (doi < 31) doi++;
+        h = H_SET_DOI(h, doi);
+        if (dl > 0) dl--;
+        h = H_SET_DL(h, dl);
+        if (dl == 0) {
+            if (sev == RB_FATAL) {                       // person_die, main.pyx:370-374, 1618-1623
+                h = H_SET_STATE(h, RB_DEAD) & ~H_LIST;
+                count_add(c, RB_A_INFECTED, age, -1); count_add(c, RB_A_DEAD, age, 1); count_add(c, RB_A_NON_HOSPITAL_DEATHS, age, 1);
+            } else if (sev >= RB_SEVERE) {               // person_hospitalize, main.pyx:321-338: the bed claim is an event
+                if (!(h & H_DET)) { h |= H_DET; count_add(c, RB_A_DETECTED, age, 1); count_add(c, RB_A_ALL_DETECTED, age, 1); }
+                uint32_t idx = atomicAdd(&c->n_events, 1u);
+                if (idx < G.cap_events) {
+                    G.ev_key[(size_t)r * G.cap_events + idx] = ((unsigned long long)sweep_pos(G, c, (uint32_t)a) << 2) | EV_HOSP_CLAIM;
+                    G.ev_agent[(size_t)r * G.cap_events + idx] = a;
+                } else set_problem(c, RB_OTHER_FAILURE);
+            } else {                                     // person_recover, main.pyx:315-318
+                h = H_SET_STATE(h, RB_RECOVERED) & ~H_LIST;
+                count_add(c, RB_A_INFECTED, age, -1); count_add(c, RB_A_RECOVERED, age, 1);
+            }
+        }
+    } else {   // HOSPITALIZED / IN_ICU
+        if (dl > 0) dl--;
+        h = H_SET_DL(h, dl);
+        if (dl == 0) {
+            int type;
+            if (st == RB_HOSPITALIZED && (sev == RB_CRITICAL || sev == RB_FATAL)) type = EV_TO_ICU;   // main.pyx:430-431
+            else {
+                // person_release_from_hospital, main.pyx:354-367: outcome does not depend on capacity
+                type = st == RB_IN_ICU ? EV_ICU_RELEASE : EV_WARD_RELEASE;
+                count_add(c, st == RB_IN_ICU ? RB_A_IN_ICU : RB_A_IN_WARD, age, -1);
+                count_add(c, RB_A_INFECTED, age, -1);
+                if (sev == RB_FATAL) { h = H_SET_STATE(h, RB_DEAD) & ~H_LIST; count_add(c, RB_A_DEAD, age, 1); count_add(c, RB_A_NON_HOSPITAL_DEATHS, age, 1); }
+                else { h = H_SET_STATE(h, RB_RECOVERED) & ~H_LIST; count_add(c, RB_A_RECOVERED, age, 1); }
+            }
+            uint32_t idx = atomicAdd(&c->n_events, 1u);
+            if (idx < G.cap_events) {
+                G.ev_key[(size_t)r * G.cap_events + idx] = ((unsigned long long)sweep_pos(G, c, (uint32_t)a) << 2) | (unsigned)type;
+                G.ev_agent[(size_t)r * G.cap_events + idx] = a;
+            } else set_problem(c, RB_OTHER_FAILURE);
+        }
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(256) k_sweep(Eng G) {
+    const int r = blockIdx.y;
+    RepCtr *c = &G.ctr[r];
+    const size_t base = (size_t)r * G.Npad;
+    const DevTable *tb = G.tables[c->epoch];
+    uint4 *hot4 = reinterpret_cast<uint4 *>(G.hot + base);
+    const int n4 = G.Npad >> 2;
+    const int lane = threadIdx.x & 31;
+    uint2 *items = G.items + (size_t)r * G.cap_items;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i - lane < n4; i += gridDim.x * blockDim.x) {
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (i < n4) w = hot4[i];
+        uint32_t hw[4] = {w.x, w.y, w.z, w.w};
+        uint32_t cnt[4] = {0, 0, 0, 0}, desc[4] = {0, 0, 0, 0};
+        bool dirty = false;
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t st = H_STATE(hw[j]);
+            any |= (st != RB_SUSCEPTIBLE) && !(st >= RB_RECOVERED && (hw[j] & H_INCL));
+        }
+        if (!__any_sync(0xffffffffu, any)) continue;
+        if (any) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) cnt[j] = advance_agent(G, r, c, tb, i * 4 + j, hw[j], dirty, desc[j]);
+            if (dirty) hot4[i] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        }
+        // contact allocation: warp prefix sum of per-lane totals, one atomic per warp (main.pyx:1554-1573 is
+        // one work item per contact slot)
+        uint32_t tot = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
+        if (wtot == 0) continue;
+        uint32_t wbase = 0;
+        if (lane == 31) { wbase = atomicAdd(&c->n_items, wtot); atomicAdd(&c->exposed_per_day, (int)wtot); }
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        uint32_t o = wbase + incl - tot;
+        if (wbase + wtot > G.cap_items) { if (lane == 31) set_problem(c, RB_OTHER_FAILURE); continue; }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            for (uint32_t s = 0; s < cnt[j]; s++) items[o++] = make_uint2((uint32_t)(i * 4 + j), desc[j] | s);
+    }
+}
+
+// ---------------------------------------------------------------- k_expose
+// One thread per sampled contact: get_one_contact (main.pyx:1290-1304), get_person_from_age_range (:1525-1535),
+// person_expose / did_infect (:238-244, 908-934).
+__global__ void __launch_bounds__(256) k_expose(Eng G) {
+    __shared__ int s_place[RB_N_PLACES];
+    const int r = blockIdx.y;
+    RepCtr *c = &G.ctr[r];
+    const size_t base = (size_t)r * G.Npad;
+    const DevTable *tb = G.tables[c->epoch];
+    const uint32_t n = min(c->n_items, G.cap_items);
+    if (blockIdx.x * blockDim.x >= n) return;
+    if (threadIdx.x < RB_N_PLACES) s_place[threadIdx.x] = 0;
+    __syncthreads();
+    const uint2 *items = G.items + (size_t)r * G.cap_items;
+    Attempt *succ = G.succ + (size_t)r * G.cap_succ;
+    const uint32_t day = (uint32_t)c->day;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint2 it = items[i];
+        uint32_t a = it.x, slot = it.y & 127u, age = (it.y >> 7) & 127u, dayidx = (it.y >> 14) & 31u;
+        bool asym = (it.y >> 19) & 1u; uint32_t var = (it.y >> 20) & 3u;
+        u32x4 x = philox(c->seed, a, day, PU_CONTACT | (slot << 8), 0);
+        double u = u01d(x.x, x.y);
+        int nrows = tb->n_rows[age];
+        const double *cum = tb->cum_p[age];
+        int lo = 0, hi = nrows;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (u < cum[mid]) hi = mid; else lo = mid + 1; }
+        int row = lo < nrows ? lo : nrows - 1;      // the reference fails here with CONTACT_PROBABILITY_FAILURE (p ~ 1e-15)
+        uint32_t t = (uint32_t)tb->start[age][row] + x.z % (uint32_t)tb->size[age][row];
+        atomicAdd(&s_place[tb->place[age][row]], 1);
+        uint32_t ht = G.hot[base + t];
+        if (H_STATE(ht) != RB_SUSCEPTIBLE) continue;
+        const rb_variant *v = &G.variants[var];
+        float si = v->iot[dayidx];
+        if (asym) si = si * v->p_asymptomatic_infection;
+        float pr = (si * v->tab[RB_T_SUSCEPTIBILITY][age_of(G, (int32_t)t)]) * v->infectiousness_multiplier;
+        u32x4 y = philox(c->seed, a, day, PU_CONTACT | (slot << 8), 1);
+        if (!chance(u01d(y.x, y.y), pr)) continue;
+        float mp = tb->mask_p[age][row];
+        if (mp != 0.0f) {
+            float ma = mp * v->p_mask_protects_others, mb = mp * v->p_mask_protects_wearer;
+            float pm = (ma + mb) - ma * mb;
+            if (chance(u01d(y.z, y.w), pm)) continue;
+        }
+        unsigned long long key = ((unsigned long long)sweep_pos(G, c, a) << 7) | slot;
+        uint32_t idx = atomicAdd(&c->n_succ, 1u);
+        if (idx < G.cap_succ) { succ[idx].cand = t; succ[idx].parent = a; succ[idx].key = key; atomicMin(&G.winner[base + t], key); }
+        else set_problem(c, RB_OTHER_FAILURE);
+    }
+    __syncthreads();
+    if (threadIdx.x < RB_N_PLACES && s_place[threadIdx.x]) atomicAdd(&c->daily_contacts[threadIdx.x], s_place[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------- k_resolve
+__global__ void __launch_bounds__(256) k_resolve(Eng G) {
+    const int r = blockIdx.y;
+    RepCtr *c = &G.ctr[r];
+    const size_t base = (size_t)r * G.Npad;
+    const uint32_t n = min(c->n_succ, G.cap_succ);
+    const Attempt *succ = G.succ + (size_t)r * G.cap_succ;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Attempt at = succ[i];
+        if (G.winner[base + at.cand] != at.key) continue;     // first infector in sweep order wins
+        device_infect(G, r, c, (int32_t)at.cand, (int32_t)at.parent, G.hot[base + at.parent], 0, (int)(at.key & 127ull), false);
+        G.winner[base + at.cand] = KEY_IDLE;
+    }
+}
+
+// ---------------------------------------------------------------- k_post
+// HealthcareSystem.hospitalize / release / to_icu / release_from_icu (main.pyx:617-651) are first-come-first-served
+// in sweep order.  Each event is a map x -> max(x + a, b) on the free-bed (and free-ICU) counter; sorting the day's
+// events by sweep position and scanning the composed maps gives every claim the counter value it would have seen.
+struct MP { int a, b; };
+__device__ __forceinline__ MP mp_compose(MP f, MP g) {   // apply f, then g
+    MP o; o.a = f.a + g.a; int t = f.b + g.a; o.b = t > g.b ? t : g.b; if (o.b < NEG_INF) o.b = NEG_INF; return o;
+}
+__device__ __forceinline__ MP mp_bed(int type) {
+    MP m; m.a = 0; m.b = NEG_INF;
+    if (type == EV_HOSP_CLAIM) { m.a = -1; m.b = 0; } else if (type == EV_WARD_RELEASE || type == EV_TO_ICU) m.a = 1;
+    return m;
+}
+__device__ __forceinline__ MP mp_icu(int type) {
+    MP m; m.a = 0; m.b = NEG_INF;
+    if (type == EV_TO_ICU) { m.a = -1; m.b = 0; } else if (type == EV_ICU_RELEASE) m.a = 1;
+    return m;
+}
+__device__ __forceinline__ int mp_apply(MP f, int x) { int t = x + f.a; return t > f.b ? t : f.b; }
+
+__global__ void __launch_bounds__(PRE_THREADS) k_post(Eng G) {
+    __shared__ unsigned long long sk[SORT_SMEM];
+    __shared__ int32_t sv[SORT_SMEM];
+    __shared__ MP s_bed[PRE_THREADS], s_icu[PRE_THREADS];
+    const int r = blockIdx.x;
+    RepCtr *c = &G.ctr[r];
+    const size_t base = (size_t)r * G.Npad;
+    const int tid = threadIdx.x;
+    const uint32_t n = min(c->n_events, G.cap_events);
+    unsigned long long *ek = G.ev_key + (size_t)r * G.cap_events;
+    int32_t *ea = G.ev_agent + (size_t)r * G.cap_events;
+    const int day = c->day;
+    if (n > 0) {
+        block_sort_pairs(ek, ea, n, G.cap_events, sk, sv);
+        __syncthreads();
+        const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+        const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
+        MP fb; fb.a = 0; fb.b = NEG_INF; MP fi = fb;
+        for (uint32_t i = lo; i < hi; i++) { int type = (int)(ek[i] & 3ull); fb = mp_compose(fb, mp_bed(type)); fi = mp_compose(fi, mp_icu(type)); }
+        s_bed[tid] = fb; s_icu[tid] = fi;
+        __syncthreads();
+        for (int o = 1; o < (int)blockDim.x; o <<= 1) {     // Hillis-Steele inclusive scan of composed maps
+            MP pb, pi; bool has = tid >= o;
+            if (has) { pb = s_bed[tid - o]; pi = s_icu[tid - o]; }
+            __syncthreads();
+            if (has) { s_bed[tid] = mp_compose(pb, s_bed[tid]); s_icu[tid] = mp_compose(pi, s_icu[tid]); }
+            __syncthreads();
+        }
+        const int beds0 = c->avail_beds, icu0 = c->avail_icu;
+        int beds = tid > 0 ? mp_apply(s_bed[tid - 1], beds0) : beds0;
+        int icu = tid > 0 ? mp_apply(s_icu[tid - 1], icu0) : icu0;
+        for (uint32_t i = lo; i < hi; i++) {
+            int type = (int)(ek[i] & 3ull);
+            int32_t a = ea[i];
+            if (type == EV_HOSP_CLAIM || type == EV_TO_ICU) {
+                uint32_t h = G.hot[base + a];
+                const uint32_t sev = H_SEV(h);
+                const rb_variant *v = &G.variants[H_VAR(h)];
+                const int age = age_of(G, a);
+                const uint32_t cold = G.cold[base + a];
+                const bool ok = type == EV_HOSP_CLAIM ? beds > 0 : icu > 0;
+                bool dies = false;
+                if (!ok) {      // Disease.dies_in_hospital(care_available=False), main.pyx:957-974
+                    if (sev == RB_FATAL) dies = true;
+                    else {
+                        float ch = sev == RB_CRITICAL ? v->p_icu_death_no_beds : (sev == RB_SEVERE ? v->p_hospital_death_no_beds : 0.0f);
+                        u32x4 x = philox(c->seed, (uint32_t)a, (uint32_t)day, PU_NOBED, 0);
+                        dies = chance(u01d(x.x, x.y), ch);
+                    }
+                }
+                if (type == EV_HOSP_CLAIM) {            // person_hospitalize, main.pyx:327-338
+                    if (ok) { h = H_SET_DL(H_SET_STATE(h, RB_HOSPITALIZED), (cold >> 16) & 255u); count_add(c, RB_A_IN_WARD, age, 1); }
+                    else {
+                        count_add(c, RB_A_INFECTED, age, -1);
+                        if (dies) { h = H_SET_STATE(h, RB_DEAD) & ~H_LIST; count_add(c, RB_A_DEAD, age, 1); if (sev == RB_FATAL) count_add(c, RB_A_NON_HOSPITAL_DEATHS, age, 1); }
+                        else { h = H_SET_STATE(h, RB_RECOVERED) & ~H_LIST; count_add(c, RB_A_RECOVERED, age, 1); }
+                    }
+                } else {                                 // person_transfer_to_icu, main.pyx:341-351
+                    count_add(c, RB_A_IN_WARD, age, -1);
+                    if (!ok && dies) {
+                        count_add(c, RB_A_INFECTED, age, -1); count_add(c, RB_A_DEAD, age, 1);
+                        if (sev == RB_FATAL) count_add(c, RB_A_NON_HOSPITAL_DEATHS, age, 1);
+                        h = H_SET_STATE(h, RB_DEAD) & ~H_LIST;
+                    } else {
+                        h = H_SET_DL(H_SET_STATE(h, RB_IN_ICU), (cold >> 24) & 255u);
+                        count_add(c, RB_A_IN_ICU, age, 1); count_add(c, RB_A_CUM_ICU, age, 1);
+                    }
+                }
+                G.hot[base + a] = h;
+            }
+            beds = mp_apply(mp_bed(type), beds);
+            icu = mp_apply(mp_icu(type), icu);
+        }
+        __syncthreads();
+        if (tid == 0) { c->avail_beds = mp_apply(s_bed[blockDim.x - 1], beds0); c->avail_icu = mp_apply(s_icu[blockDim.x - 1], icu0); }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        c->qsel ^= 1u;
+        c->n_queue = min(c->n_newq, G.cap_queue);
+        c->n_newq = 0;
+        c->day = day + 1;            // main.pyx:2009
+    }
+}
+
+// ---------------------------------------------------------------- misc kernels
+__global__ void k_init(Eng G) {
+    const int r = blockIdx.y;
+    const size_t base = (size_t)r * G.Npad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < G.Npad; i += gridDim.x * blockDim.x) {
+        // padding words beyond N are marked RECOVERED+included so that the sweep skips them
+        G.hot[base + i] = i < G.N ? 0u : (RB_RECOVERED | H_INCL);
+        G.cold[base + i] = 0; G.inf_key[base + i] = 0;
+        G.infector[base + i] = -1; G.first_child[base + i] = -1; G.next_sib[base + i] = -1;
+        G.vacc_day[base + i] = -1; G.winner[base + i] = KEY_IDLE;
+    }
+}
+
+__global__ void k_snapshot(Eng G) {
+    __shared__ int32_t srow[RB_N_ATTRS * 16 + RB_N_SCALARS];
+    write_stats_row(G, blockIdx.x, &G.ctr[blockIdx.x], srow);
+}
+
+// Context.sample, main.pyx:2047-2101
+__global__ void k_sample(Eng G, int what, int age, int severity, int n, int epoch, int32_t *out) {
+    const rb_variant *v = &G.variants[0];
+    uint32_t seed = G.ctr[0].seed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t pu = PU_SAMPLE | ((uint32_t)what << 8);
+        int res;
+        if (what == 0) {
+            float f = lognormal_half(seed, (uint32_t)i, (uint32_t)age, pu) * G.tables[epoch]->nr_contacts[age];
+            if (f < 1.0f) f = 1.0f;
+            int k = (int)f - 1; if (k > 100) k = 100;
+            res = k;
+        } else if (what == 1) {
+            u32x4 x = philox(seed, (uint32_t)i, (uint32_t)age, pu, 0);
+            res = symptom_severity(v, age, u01f(x.x), false);
+        } else if (what == 2) {
+            res = round_to_int(gamma_f(seed, (uint32_t)i, (uint32_t)age, pu, v->incubation_kappa, v->incubation_theta));
+        } else {
+            float T = severity == RB_FATAL ? gamma_f(seed, (uint32_t)i, (uint32_t)age, pu, v->onset_death_kappa, v->onset_death_theta)
+                                           : gamma_f(seed, (uint32_t)i, (uint32_t)age, pu, v->onset_recovery_kappa, v->onset_recovery_theta);
+            float f = 0.0f;
+            if (what == 3) { f = T; if (severity != RB_ASYMPTOMATIC && severity != RB_MILD) f = f * v->ratio_before_hospitalisation; }
+            else if (what == 4) { if (severity == RB_SEVERE) f = T * (1.0f - v->ratio_before_hospitalisation); else if (severity >= RB_CRITICAL) f = T * v->ratio_in_ward; }
+            else if (what == 5) { if (severity >= RB_CRITICAL) f = ((1.0f - v->ratio_in_ward) - v->ratio_before_hospitalisation) * T; }
+            else f = T;
+            res = round_to_int(f);
+        }
+        out[i] = res;
+    }
+}
+
+// ================================================================ host side / C-ABI
+static thread_local char g_err[512];
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return 1; } } while (0)
+
+struct rb_engine {
+    rb_config cfg;
+    Eng G;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    std::vector<void *> allocs;
+    std::vector<DevTable *> tables;     // host copy of the device pointer table
+    DevTable **d_tables;
+    int n_table_slots;
+    rb_day_params *d_sched;
+    std::vector<rb_day_params> h_sched;
+    std::vector<int32_t> age_start;
+    int32_t day;
+    float last_ms;
+    int64_t launches;
+    int sweep_blocks, list_blocks;
+};
+
+template <typename T> static int dalloc(rb_engine *e, T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t err = cudaMalloc(&q, n * sizeof(T));
+    if (err != cudaSuccess) { snprintf(g_err, sizeof g_err, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(err)); return 1; }
+    e->allocs.push_back(q);
+    *p = (T *)q;
+    return 0;
+}
+static uint32_t pow2_at_least(uint64_t x) { uint32_t p = 1024; while (p < x) p <<= 1; return p; }
+
+extern "C" const char *rb_last_error(void) { return g_err; }
+
+extern "C" void rb_destroy(rb_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaStreamSynchronize(e->stream);
+    for (void *p : e->allocs) cudaFree(p);
+    cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const int32_t *group_of_age,
+                         const rb_variant *variants, const int32_t *import_lo, const int32_t *import_hi,
+                         const float *import_cum, rb_engine **out) {
+    if (cfg->n_ages > RB_MAX_AGES || cfg->n_variants > RB_MAX_VARIANTS || cfg->n_import_classes > RB_MAX_IMPORT_CLASSES ||
+        cfg->n_groups > 16 || cfg->n_replicas < 1 || cfg->n_agents < 1) {
+        snprintf(g_err, sizeof g_err, "config exceeds compiled limits"); return 1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        snprintf(g_err, sizeof g_err, "no CUDA device: reina_b200 has no CPU fallback"); return 2;
+    }
+    CK(cudaSetDevice(cfg->device));
+    rb_engine *e = new rb_engine();
+    e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
+    Eng &G = e->G;
+    memset(&G, 0, sizeof G);
+    const int N = cfg->n_agents, R = cfg->n_replicas;
+    G.N = N; G.Npad = (N + 3) & ~3; G.n_ages = cfg->n_ages; G.n_groups = cfg->n_groups; G.n_variants = cfg->n_variants;
+    G.R = R; G.max_days = cfg->max_days; G.row_len = RB_N_ATTRS * cfg->n_groups + RB_N_SCALARS;
+    G.n_import_classes = cfg->n_import_classes;
+    int bits = 1; while ((1u << bits) < (uint32_t)N) bits++;
+    G.fhalf = (bits + 1) / 2;
+    e->age_start.resize(cfg->n_ages + 1);
+    int64_t tot = 0;
+    for (int a = 0; a < cfg->n_ages; a++) { e->age_start[a] = (int32_t)tot; tot += age_counts[a]; }
+    e->age_start[cfg->n_ages] = (int32_t)tot;
+    if (tot != N) { snprintf(g_err, sizeof g_err, "age_counts sum %lld != n_agents %d", (long long)tot, N); delete e; return 1; }
+    float cc = cfg->contact_capacity > 0 ? cfg->contact_capacity : 1.0f;
+    G.cap_items = pow2_at_least((uint64_t)((double)N * cc) + 4096);
+    G.cap_succ = pow2_at_least((uint64_t)N / 8 + 4096);
+    G.cap_events = pow2_at_least((uint64_t)N / 16 + 2048);
+    G.cap_queue = pow2_at_least((uint64_t)N / 8 + 2048);
+    const size_t RN = (size_t)R * G.Npad;
+    if (dalloc(e, &G.hot, RN) || dalloc(e, &G.cold, RN) || dalloc(e, &G.inf_key, RN) || dalloc(e, &G.infector, RN) ||
+        dalloc(e, &G.first_child, RN) || dalloc(e, &G.next_sib, RN) || dalloc(e, &G.vacc_day, RN) || dalloc(e, &G.winner, RN) ||
+        dalloc(e, &G.items, (size_t)R * G.cap_items) || dalloc(e, &G.succ, (size_t)R * G.cap_succ) ||
+        dalloc(e, &G.ev_key, (size_t)R * G.cap_events) || dalloc(e, &G.ev_agent, (size_t)R * G.cap_events) ||
+        dalloc(e, &G.q_key, (size_t)R * 2 * G.cap_queue) || dalloc(e, &G.q_agent, (size_t)R * 2 * G.cap_queue) ||
+        dalloc(e, &G.ctr, (size_t)R) || dalloc(e, &G.stats, (size_t)R * (cfg->max_days + 1) * G.row_len) ||
+        dalloc(e, &e->d_sched, (size_t)cfg->max_days + 1)) { rb_destroy(e); return 1; }
+    G.sched = e->d_sched;
+    e->h_sched.assign(cfg->max_days + 1, rb_day_params());
+    e->n_table_slots = 1024;
+    if (dalloc(e, &e->d_tables, (size_t)e->n_table_slots)) { rb_destroy(e); return 1; }
+    CK(cudaMemset(e->d_tables, 0, sizeof(DevTable *) * e->n_table_slots));
+    G.tables = e->d_tables;
+    e->tables.assign(e->n_table_slots, nullptr);
+    rb_variant *dv; int32_t *d_as, *d_ga, *d_ilo, *d_ihi; float *d_icum;
+    if (dalloc(e, &dv, (size_t)cfg->n_variants) || dalloc(e, &d_as, (size_t)cfg->n_ages + 1) || dalloc(e, &d_ga, (size_t)cfg->n_ages) ||
+        dalloc(e, &d_ilo, (size_t)RB_MAX_IMPORT_CLASSES) || dalloc(e, &d_ihi, (size_t)RB_MAX_IMPORT_CLASSES) ||
+        dalloc(e, &d_icum, (size_t)RB_MAX_IMPORT_CLASSES)) { rb_destroy(e); return 1; }
+    CK(cudaMemcpy(dv, variants, sizeof(rb_variant) * cfg->n_variants, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_as, e->age_start.data(), sizeof(int32_t) * (cfg->n_ages + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ga, group_of_age, sizeof(int32_t) * cfg->n_ages, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ilo, import_lo, sizeof(int32_t) * cfg->n_import_classes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ihi, import_hi, sizeof(int32_t) * cfg->n_import_classes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_icum, import_cum, sizeof(float) * cfg->n_import_classes, cudaMemcpyHostToDevice));
+    G.variants = dv; G.age_start = d_as; G.group_of_age = d_ga; G.import_lo = d_ilo; G.import_hi = d_ihi; G.import_cum = d_icum;
+    // per-replica counters
+    std::vector<RepCtr> hc(R);
+    memset(hc.data(), 0, sizeof(RepCtr) * R);
+    for (int r = 0; r < R; r++) {
+        RepCtr &c = hc[r];
+        for (int a = 0; a < cfg->n_ages; a++) c.counts[RB_A_SUSCEPTIBLE][a] = age_counts[a];
+        c.beds = c.avail_beds = cfg->hospital_beds; c.icu = c.avail_icu = cfg->icu_units;
+        c.p_successful_tracing = 1.0f;
+        c.seed = cfg->seed + (uint32_t)r;
+        u32x4 k = philox(c.seed, 0, 0, PU_PERM, 0);
+        c.fkey[0] = k.x; c.fkey[1] = k.y; c.fkey[2] = k.z; c.fkey[3] = k.w;
+        for (int i = 0; i < RB_MAX_VACC; i++) c.vacc_cursor[i] = -2;
+    }
+    CK(cudaMemcpy(G.ctr, hc.data(), sizeof(RepCtr) * R, cudaMemcpyHostToDevice));
+    CK(cudaMemset(G.stats, 0, sizeof(int32_t) * (size_t)R * (cfg->max_days + 1) * G.row_len));
+    CK(cudaMemset(e->d_sched, 0, sizeof(rb_day_params) * ((size_t)cfg->max_days + 1)));
+    // launch geometry: grid-stride kernels sized in multiples of the SM count
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
+    int sms = prop.multiProcessorCount;
+    int want = (G.Npad / 4 + 255) / 256;
+    int per_rep = (sms * 8 + R - 1) / R; if (per_rep < 4) per_rep = 4;
+    e->sweep_blocks = want < per_rep ? want : per_rep; if (e->sweep_blocks < 1) e->sweep_blocks = 1;
+    e->list_blocks = (sms * 4 + R - 1) / R; if (e->list_blocks < 2) e->list_blocks = 2;
+    k_init<<<dim3(e->sweep_blocks, R), 256, 0, e->stream>>>(G); e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    *out = e;
+    return 0;
+}
+
+extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *n_rows, const double *cum_p,
+                                    const int32_t *age_lo, const int32_t *age_hi, const uint8_t *place,
+                                    const float *mask_p, const double *nr_contacts) {
+    if (epoch < 0 || epoch >= e->n_table_slots) { snprintf(g_err, sizeof g_err, "table epoch out of range"); return 1; }
+    CK(cudaSetDevice(e->cfg.device));
+    DevTable *h = new DevTable();
+    memset(h, 0, sizeof *h);
+    for (int age = 0; age < e->cfg.n_ages; age++) {
+        h->n_rows[age] = n_rows[age];
+        h->nr_contacts[age] = (float)nr_contacts[age];
+        for (int i = 0; i < n_rows[age]; i++) {
+            int k = age * RB_MAX_ROWS + i;
+            h->cum_p[age][i] = cum_p[k];
+            h->start[age][i] = e->age_start[age_lo[k]];
+            h->size[age][i] = e->age_start[age_hi[k] + 1] - e->age_start[age_lo[k]];
+            h->place[age][i] = place[k];
+            h->mask_p[age][i] = mask_p[k];
+        }
+    }
+    DevTable *d = e->tables[epoch];
+    if (!d) { if (dalloc(e, &d, 1)) { delete h; return 1; } e->tables[epoch] = d; }
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(d, h, sizeof(DevTable), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_tables + epoch, &d, sizeof(DevTable *), cudaMemcpyHostToDevice));
+    delete h;
+    return 0;
+}
+
+extern "C" int rb_set_schedule(rb_engine *e, int32_t day0, int32_t n, const rb_day_params *params) {
+    if (day0 < 0 || day0 + n > e->cfg.max_days + 1) { snprintf(g_err, sizeof g_err, "schedule out of range"); return 1; }
+    CK(cudaSetDevice(e->cfg.device));
+    memcpy(e->h_sched.data() + day0, params, sizeof(rb_day_params) * n);
+    CK(cudaMemcpyAsync(e->d_sched + day0, e->h_sched.data() + day0, sizeof(rb_day_params) * n, cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+
+extern "C" int rb_step(rb_engine *e, int32_t n_days) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->day + n_days > e->cfg.max_days) { snprintf(g_err, sizeof g_err, "max_days exceeded"); return 1; }
+    for (int d = 0; d < n_days; d++) {
+        int ep = e->h_sched[e->day + d].table_epoch;
+        if (ep < 0 || ep >= e->n_table_slots || !e->tables[ep]) { snprintf(g_err, sizeof g_err, "contact table %d not set", ep); return 1; }
+    }
+    const Eng &G = e->G;
+    const int R = G.R;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    for (int d = 0; d < n_days; d++) {
+        k_pre<<<R, PRE_THREADS, 0, e->stream>>>(G);
+        k_sweep<<<dim3(e->sweep_blocks, R), 256, 0, e->stream>>>(G);
+        k_expose<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G);
+        k_resolve<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G);
+        k_post<<<R, PRE_THREADS, 0, e->stream>>>(G);
+        e->launches += 5;
+    }
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaGetLastError());
+    e->day += n_days;
+    return 0;
+}
+
+extern "C" int rb_sync(rb_engine *e) {
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_ms = ms; else cudaGetLastError();
+    return 0;
+}
+
+extern "C" int32_t rb_day(rb_engine *e) { return e->day; }
+extern "C" int32_t rb_row_len(rb_engine *e) { return e->G.row_len; }
+extern "C" float rb_last_step_ms(rb_engine *e) { return e->last_ms; }
+extern "C" int64_t rb_launch_count(rb_engine *e) { return e->launches; }
+
+extern "C" int rb_snapshot(rb_engine *e) {
+    CK(cudaSetDevice(e->cfg.device));
+    k_snapshot<<<e->G.R, 256, 0, e->stream>>>(e->G); e->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rb_read_stats(rb_engine *e, int32_t day0, int32_t n, int32_t *out) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (day0 < 0 || day0 + n > e->cfg.max_days + 1) { snprintf(g_err, sizeof g_err, "stats range"); return 1; }
+    const Eng &G = e->G;
+    CK(cudaMemcpy2DAsync(out, sizeof(int32_t) * (size_t)n * G.row_len,
+                         G.stats + (size_t)day0 * G.row_len, sizeof(int32_t) * (size_t)(G.max_days + 1) * G.row_len,
+                         sizeof(int32_t) * (size_t)n * G.row_len, G.R, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int rb_read_per_age(rb_engine *e, int32_t replica, int32_t attr, int32_t *out) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (replica < 0 || replica >= e->G.R || attr < 0 || attr >= RB_N_ATTRS) { snprintf(g_err, sizeof g_err, "bad replica/attr"); return 1; }
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out, &e->G.ctr[replica].counts[attr][0], sizeof(int32_t) * e->cfg.n_ages, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int rb_problem(rb_engine *e, int32_t *out) {
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int r = 0; r < e->G.R; r++) CK(cudaMemcpy(out + r, &e->G.ctr[r].problem, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int rb_sample(rb_engine *e, int32_t what, int32_t age, int32_t severity, int32_t n, int32_t *out) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (what < 0 || what > 6 || age < 0 || age >= e->cfg.n_ages) { snprintf(g_err, sizeof g_err, "bad sample request"); return 1; }
+    int32_t *d; CK(cudaMalloc(&d, sizeof(int32_t) * n));
+    int epoch = e->h_sched[e->day > 0 ? e->day - 1 : 0].table_epoch;
+    k_sample<<<(n + 255) / 256, 256, 0, e->stream>>>(e->G, what, age, severity, n, epoch, d); e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out, d, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
+
+extern "C" int rb_read_agents(rb_engine *e, int32_t replica, rb_agent *out) {
+    CK(cudaSetDevice(e->cfg.device));
+    const Eng &G = e->G;
+    if (replica < 0 || replica >= G.R) { snprintf(g_err, sizeof g_err, "bad replica"); return 1; }
+    CK(cudaStreamSynchronize(e->stream));
+    const int N = G.N; const size_t base = (size_t)replica * G.Npad;
+    std::vector<uint32_t> hot(N), cold(N); std::vector<int32_t> inf(N); std::vector<int16_t> vd(N);
+    CK(cudaMemcpy(hot.data(), G.hot + base, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cold.data(), G.cold + base, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(inf.data(), G.infector + base, sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(vd.data(), G.vacc_day + base, sizeof(int16_t) * N, cudaMemcpyDeviceToHost));
+    for (int a = 0; a < N; a++) {
+        uint32_t h = hot[a]; rb_agent *o = &out[a];
+        o->infector = inf[a]; o->n_infected = (int32_t)(cold[a] & 0xffffu);
+        o->days_left = (int16_t)H_DL(h); o->day_of_illness = (int16_t)H_DOI(h); o->day_of_vaccination = vd[a];
+        o->state = (uint8_t)H_STATE(h); o->severity = (uint8_t)H_SEV(h); o->variant = (uint8_t)H_VAR(h);
+        o->flags = (uint8_t)(((h & H_DET) ? 1 : 0) | ((h & H_QUEUED) ? 2 : 0) | ((h & H_INCL) ? 4 : 0) | ((h & H_LIST) ? 8 : 0));
+        o->ward_days = (uint8_t)((cold[a] >> 16) & 255u); o->icu_days = (uint8_t)((cold[a] >> 24) & 255u);
+    }
+    return 0;
+}
+
+extern "C" int rb_read_queue(rb_engine *e, int32_t replica, int32_t *out, int32_t cap, int32_t *n) {
+    CK(cudaSetDevice(e->cfg.device));
+    const Eng &G = e->G;
+    CK(cudaStreamSynchronize(e->stream));
+    RepCtr c; CK(cudaMemcpy(&c, &G.ctr[replica], sizeof c, cudaMemcpyDeviceToHost));
+    *n = (int32_t)c.n_queue;
+    int m = (int)c.n_queue < cap ? (int)c.n_queue : cap;
+    if (m > 0) CK(cudaMemcpy(out, G.q_agent + ((size_t)replica * 2 + c.qsel) * G.cap_queue, sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int rb_read_available(rb_engine *e, int32_t replica, int32_t *o) {
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    RepCtr c; CK(cudaMemcpy(&c, &e->G.ctr[replica], sizeof c, cudaMemcpyDeviceToHost));
+    o[0] = c.avail_beds; o[1] = c.avail_icu;
+    return 0;
+}

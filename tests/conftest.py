@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+@pytest.fixture(scope='session')
+def oracle_lib():
+    import helpers
+    return helpers.oracle_library()
+
+
+@pytest.fixture(scope='session')
+def cuda_lib():
+    import helpers
+    return helpers.cuda_library()

@@ -83,3 +83,68 @@ def series_matrix(ctx, days=None):
 def series_names(variant_names=('wild-type', 'b1.1.7')):
     return (POP_SERIES + SCALAR_SERIES + ['exposures_%s' % p for p in PLACES]
             + ['infected_by_variant_%s' % v for v in variant_names])
+
+
+# ---------------------------------------------------------------------------------------------------
+# parity utilities
+# ---------------------------------------------------------------------------------------------------
+def scaled_capacity(n_agents, beds=2600, icu=300, full=1685983):
+    """Hospital capacity scaled with the population so that small test populations still saturate."""
+    return max(1, round(beds * n_agents / full)), max(1, round(icu * n_agents / full))
+
+
+def stress_interventions():
+    """A schedule that exercises every intervention type early: imports of both variants, weekly trickle
+    with a variant share, every testing mode, contact tracing, masks, place/age mobility limits,
+    vaccination programmes and capacity building."""
+    T = [
+        ['import-infections', '2020-02-18', 150],
+        ['import-infections', '2020-02-18', 60, 'b1.1.7'],
+        ['test-all-with-symptoms', '2020-02-20'],
+        ['import-infections-weekly', '2020-02-21', 40, 30],
+        ['limit-mobility', '2020-02-25', 20],
+        ['test-only-severe-symptoms', '2020-02-27', 40],
+        ['wear-masks', '2020-02-28', 60, 15, None, None],
+        ['limit-mobility', '2020-03-01', 50, 7, 18, 'school'],
+        ['test-with-contact-tracing', '2020-03-04', 60],
+        ['vaccinate', '2020-03-05', 700, 70, None],
+        ['vaccinate', '2020-03-08', 1400, 16, 69],
+        ['import-infections', '2020-03-10', 100],
+        ['limit-mobility', '2020-03-12', 0],
+        ['wear-masks', '2020-03-12', 90, None, None, 'transport'],
+        ['build-new-hospital-beds', '2020-03-20', 3],
+        ['build-new-icu-units', '2020-03-20', 1],
+        ['test-with-contact-tracing', '2020-03-25', 100],
+        ['vaccinate', '2020-03-28', 2100, 70, None],
+        ['test-all-with-symptoms', '2020-04-10'],
+        ['test-with-contact-tracing', '2020-04-20', 35],
+    ]
+    from reina_b200 import inputs as _inputs
+    return [_inputs.iv_tuple_to_obj(t) for t in T]
+
+
+def diff_report(gpu, cpu, days):
+    """Compare two contexts after the same run; returns a list of human-readable differences (empty = equal)."""
+    out = []
+    a, b = gpu.series(0, days), cpu.series(0, days)
+    names = gpu.row_layout()
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        r, d, col = bad[0]
+        cols = sorted({names[c] for c in bad[bad[:, 1] == d][:, 2]})
+        out.append('stats differ at %d cells; first: replica %d day %d col %s gpu=%d cpu=%d; columns that day: %s'
+                   % (len(bad), r, d, names[col], a[r, d, col], b[r, d, col], cols[:12]))
+    for r in range(gpu.n_replicas):
+        ga, ca = gpu._engine.read_agents(r), cpu._engine.read_agents(r)
+        if not np.array_equal(ga, ca):
+            for f in ga.dtype.names:
+                if not np.array_equal(ga[f], ca[f]):
+                    idx = np.flatnonzero(ga[f] != ca[f])
+                    out.append('replica %d agent field %s differs for %d agents, first %d: gpu=%s cpu=%s'
+                               % (r, f, len(idx), idx[0], ga[f][idx[0]], ca[f][idx[0]]))
+        gq, cq = gpu._engine.read_queue(r), cpu._engine.read_queue(r)
+        if sorted(gq.tolist()) != sorted(cq.tolist()):
+            out.append('replica %d test queue differs: gpu %d entries, cpu %d' % (r, len(gq), len(cq)))
+        if not np.array_equal(gpu._engine.read_available(r), cpu._engine.read_available(r)):
+            out.append('replica %d free beds/icu differ' % r)
+    return out
