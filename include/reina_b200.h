@@ -126,6 +126,10 @@ int rb_create(const rb_config *cfg, const int32_t *age_counts, const int32_t *gr
               const float *import_cum, rb_engine **out);
 void rb_destroy(rb_engine *e);
 
+/* Re-initialise every replica to the state right after rb_create with a new base seed (a fresh
+ * Context(random_seed=seed), main.pyx:1759-1781) without reallocating; schedule and contact tables are kept. */
+int rb_reset(rb_engine *e, uint32_t seed);
+
 /* ContactMatrix.generate_contact_probabilities output (main.pyx:1184-1235) for one mobility epoch:
  * per participant age `n_rows[age]` rows of {cum_p, contact band [lo,hi], place, mask_p}, arrays are
  * [n_ages][RB_MAX_ROWS]; nr_contacts[age] = nr_contacts_by_age (main.pyx:1209-1211). */
@@ -165,6 +169,10 @@ int rb_read_queue(rb_engine *e, int32_t replica, int32_t *out, int32_t cap, int3
 int rb_read_available(rb_engine *e, int32_t replica, int32_t *beds_icu);  /* {available_beds, available_icu_units} */
 /* timing of the last rb_step measured with CUDA events on the handle's stream (ms); oracle: wall clock */
 float rb_last_step_ms(rb_engine *e);
+/* Like rb_step, but brackets every kernel with CUDA events and returns the summed device time per kernel
+ * (ms_per_kernel[RB_N_KERNELS], order: pre, sweep, expose, resolve, post).  Measurement aid for bench.py. */
+#define RB_N_KERNELS 5
+int rb_step_profiled(rb_engine *e, int32_t n_days, float *ms_per_kernel);
 /* number of kernel launches issued by this handle so far */
 int64_t rb_launch_count(rb_engine *e);
 const char *rb_last_error(void);

@@ -612,6 +612,7 @@ static void iterate_replica(rb_engine *e, int ri) {
 }
 
 /* ------------------------------------------------------------------ C-ABI (ro_ mirrors rb_) */
+static void init_replica(rb_engine *e, int ri, uint32_t seed);
 int ro_create(const rb_config *cfg, const int32_t *age_counts, const int32_t *group_of_age,
               const rb_variant *variants, const int32_t *import_lo, const int32_t *import_hi,
               const float *import_cum, rb_engine **out) {
@@ -633,28 +634,46 @@ int ro_create(const rb_config *cfg, const int32_t *age_counts, const int32_t *gr
     int bits = 1; while ((1u << bits) < (uint32_t)cfg->n_agents) bits++;
     e->feistel_half = (bits + 1) / 2;
     e->rep = (Replica *)calloc(cfg->n_replicas, sizeof(Replica));
-    for (int ri = 0; ri < cfg->n_replicas; ri++) {
-        Replica *r = &e->rep[ri];
-        r->seed = cfg->seed + (uint32_t)ri;
-        r->agents = (Agent *)calloc(cfg->n_agents, sizeof(Agent));
-        r->order = (int32_t *)malloc(sizeof(int32_t) * cfg->n_agents);
-        r->perm = (int32_t *)malloc(sizeof(int32_t) * cfg->n_agents);
-        philox(r->seed, KEY1, 0, 0, PU_PERM, 0, r->fkey);
-        for (int age = 0; age < cfg->n_ages; age++) {
-            r->counts[RB_A_SUSCEPTIBLE][age] = age_counts[age];
-            for (int32_t a = e->age_start[age]; a < e->age_start[age + 1]; a++) {
-                Agent *p = &r->agents[a];
-                p->age = (uint8_t)age; p->infector = -1; p->day_of_vaccination = -1; p->day_of_infection = -1;
-                uint32_t s = feistel((uint32_t)a, (uint32_t)cfg->n_agents, e->feistel_half, r->fkey);
-                r->perm[a] = (int32_t)s; r->order[s] = a;
-            }
-        }
-        r->beds = r->avail_beds = cfg->hospital_beds;
-        r->icu = r->avail_icu = cfg->icu_units;
-        r->p_successful_tracing = 1.0f;
-    }
+    for (int ri = 0; ri < cfg->n_replicas; ri++) init_replica(e, ri, cfg->seed);
     *out = e;
     return 0;
+}
+
+static void init_replica(rb_engine *e, int ri, uint32_t seed) {
+    const rb_config *cfg = &e->cfg;
+    Replica *r = &e->rep[ri];
+    if (r->agents) for (int32_t a = 0; a < cfg->n_agents; a++) free(r->agents[a].infectees);
+    free(r->agents); free(r->order); free(r->perm); free(r->queue); free(r->newq);
+    memset(r, 0, sizeof *r);
+    r->seed = seed + (uint32_t)ri;
+    r->agents = (Agent *)calloc(cfg->n_agents, sizeof(Agent));
+    r->order = (int32_t *)malloc(sizeof(int32_t) * cfg->n_agents);
+    r->perm = (int32_t *)malloc(sizeof(int32_t) * cfg->n_agents);
+    philox(r->seed, KEY1, 0, 0, PU_PERM, 0, r->fkey);
+    for (int age = 0; age < cfg->n_ages; age++) {
+        r->counts[RB_A_SUSCEPTIBLE][age] = e->age_start[age + 1] - e->age_start[age];
+        for (int32_t a = e->age_start[age]; a < e->age_start[age + 1]; a++) {
+            Agent *p = &r->agents[a];
+            p->age = (uint8_t)age; p->infector = -1; p->day_of_vaccination = -1; p->day_of_infection = -1;
+            uint32_t s = feistel((uint32_t)a, (uint32_t)cfg->n_agents, e->feistel_half, r->fkey);
+            r->perm[a] = (int32_t)s; r->order[s] = a;
+        }
+    }
+    r->beds = r->avail_beds = cfg->hospital_beds;
+    r->icu = r->avail_icu = cfg->icu_units;
+    r->p_successful_tracing = 1.0f;
+}
+
+int ro_reset(rb_engine *e, uint32_t seed) {
+    e->cfg.seed = seed; e->day = 0;
+    for (int ri = 0; ri < e->cfg.n_replicas; ri++) init_replica(e, ri, seed);
+    return 0;
+}
+
+int ro_step(rb_engine *e, int32_t n_days);
+int ro_step_profiled(rb_engine *e, int32_t n_days, float *ms) {
+    for (int k = 0; k < RB_N_KERNELS; k++) ms[k] = 0;
+    return ro_step(e, n_days);
 }
 
 void ro_destroy(rb_engine *e) {

@@ -80,7 +80,7 @@ assert AGENT_DTYPE.itemsize == 20, AGENT_DTYPE.itemsize
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CUDA_LIB_PATH = os.path.join(_HERE, 'libreina_b200.so')
 
-SYMBOLS = ['create', 'destroy', 'set_contact_table', 'set_schedule', 'step', 'sync', 'day',
+SYMBOLS = ['create', 'destroy', 'reset', 'step_profiled', 'set_contact_table', 'set_schedule', 'step', 'sync', 'day',
            'snapshot', 'row_len', 'read_stats', 'read_per_age', 'problem', 'sample', 'read_agents',
            'read_queue', 'read_available', 'last_step_ms', 'launch_count', 'last_error']
 
@@ -118,6 +118,8 @@ class Library:
                                            C.POINTER(C.c_double)]
         f['set_schedule'].argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(DayParams)]
         f['step'].argtypes = [vp, C.c_int32]
+        f['reset'].argtypes = [vp, C.c_uint32]
+        f['step_profiled'].argtypes = [vp, C.c_int32, C.POINTER(C.c_float)]
         f['sync'].argtypes = [vp]
         f['day'].argtypes = [vp]
         f['day'].restype = C.c_int32
@@ -201,6 +203,14 @@ class Engine:
 
     def step(self, n=1):
         self.lib.check(self.lib.f['step'](self.h, n), 'step')
+
+    def reset(self, seed):
+        self.lib.check(self.lib.f['reset'](self.h, int(seed) & 0xFFFFFFFF), 'reset')
+
+    def step_profiled(self, n):
+        out = np.zeros(5, dtype=np.float32)
+        self.lib.check(self.lib.f['step_profiled'](self.h, n, _ptr(out, C.c_float)), 'step_profiled')
+        return out
 
     def sync(self):
         self.lib.check(self.lib.f['sync'](self.h), 'sync')

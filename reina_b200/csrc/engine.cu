@@ -310,14 +310,21 @@ __device__ __forceinline__ bool trace_eligible(uint32_t h) {   // queue_for_test
     return H_STATE(h) != RB_DEAD && !(h & (H_DET | H_QUEUED));
 }
 
-// ---------------------------------------------------------------- k_pre
-__global__ void __launch_bounds__(PRE_THREADS) k_pre(Eng G) {
-    __shared__ unsigned long long sk[SORT_SMEM];
-    __shared__ int32_t sv[SORT_SMEM];
-    __shared__ int32_t srow[RB_N_ATTRS * 16 + RB_N_SCALARS];
-    __shared__ int warp_sums[32];
-    __shared__ int sh_i[4];
-    const int r = blockIdx.x;
+// ---------------------------------------------------------------- day boundary (1 CTA per replica)
+struct MP { int a, b; };
+struct SmemSmall {
+    unsigned long long sk[SORT_SMEM];
+    int32_t sv[SORT_SMEM];
+    union {
+        int32_t srow[RB_N_ATTRS * 16 + RB_N_SCALARS];
+        struct { MP bed[PRE_THREADS], icu[PRE_THREADS]; } scan;
+    } u;
+    int warp_sums[32];
+    int sh_i[4];
+};
+
+__device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
+    unsigned long long *sk = S.sk; int32_t *sv = S.sv; int32_t *srow = S.u.srow; int *warp_sums = S.warp_sums; int *sh_i = S.sh_i;
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
     const int day = c->day;
@@ -638,49 +645,82 @@ __device__ __forceinline__ uint32_t advance_agent(const Eng &G, int r, RepCtr *c
     return n;
 }
 
-__global__ void __launch_bounds__(256) k_sweep(Eng G) {
+// The daily sweep streams the packed words tile by tile (coalesced 16-byte loads), compacts the few agents that
+// have anything to do today into shared memory, and only then runs the state machine on the compacted list, so the
+// branchy part executes with full warps.  Contact work items are allocated with one block-level prefix sum and one
+// atomic per tile and written cooperatively (coalesced).
+#define SW_THREADS 256
+#define SW_TILE 2048
+__global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
+    __shared__ uint32_t s_idx[SW_TILE];     // tile-local index of each active agent
+    __shared__ uint32_t s_word[SW_TILE];    // its packed word; later the exclusive prefix of contact counts
+    __shared__ uint32_t s_desc[SW_TILE];    // contact descriptor (age, infectiousness day, asymptomatic, variant)
+    __shared__ int warp_sums[32];
+    __shared__ uint32_t s_n[3];             // rotating counters: reset two iterations ahead, between barriers
+    __shared__ uint32_t s_base;
     const int r = blockIdx.y;
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
     const DevTable *tb = G.tables[c->epoch];
-    uint4 *hot4 = reinterpret_cast<uint4 *>(G.hot + base);
-    const int n4 = G.Npad >> 2;
-    const int lane = threadIdx.x & 31;
+    const uint4 *hot4 = reinterpret_cast<const uint4 *>(G.hot + base);
     uint2 *items = G.items + (size_t)r * G.cap_items;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i - lane < n4; i += gridDim.x * blockDim.x) {
-        uint4 w = make_uint4(0, 0, 0, 0);
-        if (i < n4) w = hot4[i];
-        uint32_t hw[4] = {w.x, w.y, w.z, w.w};
-        uint32_t cnt[4] = {0, 0, 0, 0}, desc[4] = {0, 0, 0, 0};
-        bool dirty = false;
-        bool any = false;
+    const int tid = threadIdx.x;
+    const int n_tiles = (G.Npad + SW_TILE - 1) / SW_TILE;
+    if (tid < 3) s_n[tid] = 0;
+    __syncthreads();
+    int par = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par = par == 2 ? 0 : par + 1) {
+        const int t0 = tile * SW_TILE;
+        // phase 1: stream + compact
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t st = H_STATE(hw[j]);
-            any |= (st != RB_SUSCEPTIBLE) && !(st >= RB_RECOVERED && (hw[j] & H_INCL));
+        for (int q = 0; q < SW_TILE / (SW_THREADS * 4); q++) {
+            int li = q * SW_THREADS * 4 + tid * 4;
+            if (t0 + li < G.Npad) {
+                uint4 w = __ldg(&hot4[(t0 + li) >> 2]);
+                uint32_t hw[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t st = H_STATE(hw[j]);
+                    if (st != RB_SUSCEPTIBLE && !(st >= RB_RECOVERED && (hw[j] & H_INCL))) {
+                        uint32_t p = atomicAdd(&s_n[par], 1u);
+                        s_idx[p] = (uint32_t)(li + j); s_word[p] = hw[j];
+                    }
+                }
+            }
         }
-        if (!__any_sync(0xffffffffu, any)) continue;
-        if (any) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) cnt[j] = advance_agent(G, r, c, tb, i * 4 + j, hw[j], dirty, desc[j]);
-            if (dirty) hot4[i] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        __syncthreads();
+        const uint32_t n = s_n[par];
+        if (tid == 0) s_n[par == 0 ? 2 : par - 1] = 0;      // (i + 2) % 3: last read before this barrier, next used after the next one
+        if (n == 0) continue;
+        // phase 2: state machine on the compacted list (thread k owns entries k*per .. so that the scan is local)
+        const uint32_t per = (n + SW_THREADS - 1) / SW_THREADS;
+        const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
+        uint32_t mine = 0;
+        for (uint32_t k = lo; k < hi; k++) {
+            int32_t a = t0 + (int32_t)s_idx[k];
+            uint32_t h = s_word[k], desc = 0; bool dirty = false;
+            uint32_t cnt = advance_agent(G, r, c, tb, a, h, dirty, desc);
+            if (dirty) G.hot[base + a] = h;
+            s_desc[k] = desc;
+            s_word[k] = cnt;
+            mine += cnt;
         }
-        // contact allocation: warp prefix sum of per-lane totals, one atomic per warp (main.pyx:1554-1573 is
-        // one work item per contact slot)
-        uint32_t tot = cnt[0] + cnt[1] + cnt[2] + cnt[3];
-        uint32_t incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
-        if (wtot == 0) continue;
-        uint32_t wbase = 0;
-        if (lane == 31) { wbase = atomicAdd(&c->n_items, wtot); atomicAdd(&c->exposed_per_day, (int)wtot); }
-        wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        uint32_t o = wbase + incl - tot;
-        if (wbase + wtot > G.cap_items) { if (lane == 31) set_problem(c, RB_OTHER_FAILURE); continue; }
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            for (uint32_t s = 0; s < cnt[j]; s++) items[o++] = make_uint2((uint32_t)(i * 4 + j), desc[j] | s);
+        int total;
+        int incl = block_scan_incl((int)mine, &total, warp_sums);
+        if (total == 0) { __syncthreads(); continue; }
+        uint32_t run = (uint32_t)incl - mine;
+        for (uint32_t k = lo; k < hi; k++) { uint32_t cnt = s_word[k]; s_word[k] = run; run += cnt; }
+        if (tid == 0) { s_base = atomicAdd(&c->n_items, (uint32_t)total); atomicAdd(&c->exposed_per_day, total); }
+        __syncthreads();
+        const uint32_t gbase = s_base;
+        if (gbase + (uint32_t)total > G.cap_items) { if (tid == 0) set_problem(c, RB_OTHER_FAILURE); __syncthreads(); continue; }
+        // phase 3: one work item per contact slot, written cooperatively
+        for (uint32_t t = tid; t < (uint32_t)total; t += SW_THREADS) {
+            uint32_t a0 = 0, b0 = n;                  // largest k with prefix[k] <= t
+            while (b0 - a0 > 1) { uint32_t mid = (a0 + b0) >> 1; if (s_word[mid] <= t) a0 = mid; else b0 = mid; }
+            items[gbase + t] = make_uint2((uint32_t)t0 + s_idx[a0], s_desc[a0] | (t - s_word[a0]));
+        }
+        __syncthreads();
     }
 }
 
@@ -755,7 +795,6 @@ __global__ void __launch_bounds__(256) k_resolve(Eng G) {
 // HealthcareSystem.hospitalize / release / to_icu / release_from_icu (main.pyx:617-651) are first-come-first-served
 // in sweep order.  Each event is a map x -> max(x + a, b) on the free-bed (and free-ICU) counter; sorting the day's
 // events by sweep position and scanning the composed maps gives every claim the counter value it would have seen.
-struct MP { int a, b; };
 __device__ __forceinline__ MP mp_compose(MP f, MP g) {   // apply f, then g
     MP o; o.a = f.a + g.a; int t = f.b + g.a; o.b = t > g.b ? t : g.b; if (o.b < NEG_INF) o.b = NEG_INF; return o;
 }
@@ -771,11 +810,8 @@ __device__ __forceinline__ MP mp_icu(int type) {
 }
 __device__ __forceinline__ int mp_apply(MP f, int x) { int t = x + f.a; return t > f.b ? t : f.b; }
 
-__global__ void __launch_bounds__(PRE_THREADS) k_post(Eng G) {
-    __shared__ unsigned long long sk[SORT_SMEM];
-    __shared__ int32_t sv[SORT_SMEM];
-    __shared__ MP s_bed[PRE_THREADS], s_icu[PRE_THREADS];
-    const int r = blockIdx.x;
+__device__ void post_body(const Eng &G, const int r, SmemSmall &S) {
+    unsigned long long *sk = S.sk; int32_t *sv = S.sv; MP *s_bed = S.u.scan.bed, *s_icu = S.u.scan.icu;
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
     const int tid = threadIdx.x;
@@ -856,6 +892,16 @@ __global__ void __launch_bounds__(PRE_THREADS) k_post(Eng G) {
     }
 }
 
+__global__ void __launch_bounds__(PRE_THREADS) k_pre(Eng G) { __shared__ SmemSmall S; pre_body(G, blockIdx.x, S); }
+__global__ void __launch_bounds__(PRE_THREADS) k_post(Eng G) { __shared__ SmemSmall S; post_body(G, blockIdx.x, S); }
+// end of day d (capacity scan) fused with the start of day d+1 (stats row, queue, tracing, ...): one launch less per day
+__global__ void __launch_bounds__(PRE_THREADS) k_between(Eng G) {
+    __shared__ SmemSmall S;
+    post_body(G, blockIdx.x, S);
+    __syncthreads();
+    pre_body(G, blockIdx.x, S);
+}
+
 // ---------------------------------------------------------------- misc kernels
 __global__ void k_init(Eng G) {
     const int r = blockIdx.y;
@@ -920,11 +966,13 @@ struct rb_engine {
     int n_table_slots;
     rb_day_params *d_sched;
     std::vector<rb_day_params> h_sched;
-    std::vector<int32_t> age_start;
+    std::vector<int32_t> age_start, age_counts;
     int32_t day;
     float last_ms;
     int64_t launches;
     int sweep_blocks, list_blocks;
+    cudaGraphExec_t graph[2];
+    bool have_graphs;
 };
 
 template <typename T> static int dalloc(rb_engine *e, T **p, size_t n) {
@@ -939,10 +987,31 @@ static uint32_t pow2_at_least(uint64_t x) { uint32_t p = 1024; while (p < x) p <
 
 extern "C" const char *rb_last_error(void) { return g_err; }
 
+static int init_counters(rb_engine *e, uint32_t seed) {
+    const rb_config *cfg = &e->cfg;
+    const int R = cfg->n_replicas;
+    std::vector<RepCtr> hc(R);
+    memset(hc.data(), 0, sizeof(RepCtr) * R);
+    for (int r = 0; r < R; r++) {
+        RepCtr &c = hc[r];
+        for (int a = 0; a < cfg->n_ages; a++) c.counts[RB_A_SUSCEPTIBLE][a] = e->age_counts[a];
+        c.beds = c.avail_beds = cfg->hospital_beds; c.icu = c.avail_icu = cfg->icu_units;
+        c.p_successful_tracing = 1.0f;
+        c.seed = seed + (uint32_t)r;
+        u32x4 k = philox(c.seed, 0, 0, PU_PERM, 0);
+        c.fkey[0] = k.x; c.fkey[1] = k.y; c.fkey[2] = k.z; c.fkey[3] = k.w;
+        for (int i = 0; i < RB_MAX_VACC; i++) c.vacc_cursor[i] = -2;
+    }
+    CK(cudaMemcpyAsync(e->G.ctr, hc.data(), sizeof(RepCtr) * R, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
 extern "C" void rb_destroy(rb_engine *e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
+    if (e->have_graphs) { cudaGraphExecDestroy(e->graph[0]); cudaGraphExecDestroy(e->graph[1]); }
     for (void *p : e->allocs) cudaFree(p);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaStreamDestroy(e->stream);
@@ -962,7 +1031,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     }
     CK(cudaSetDevice(cfg->device));
     rb_engine *e = new rb_engine();
-    e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0;
+    e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0; e->have_graphs = false;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     Eng &G = e->G;
@@ -1009,26 +1078,14 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     CK(cudaMemcpy(d_ihi, import_hi, sizeof(int32_t) * cfg->n_import_classes, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_icum, import_cum, sizeof(float) * cfg->n_import_classes, cudaMemcpyHostToDevice));
     G.variants = dv; G.age_start = d_as; G.group_of_age = d_ga; G.import_lo = d_ilo; G.import_hi = d_ihi; G.import_cum = d_icum;
-    // per-replica counters
-    std::vector<RepCtr> hc(R);
-    memset(hc.data(), 0, sizeof(RepCtr) * R);
-    for (int r = 0; r < R; r++) {
-        RepCtr &c = hc[r];
-        for (int a = 0; a < cfg->n_ages; a++) c.counts[RB_A_SUSCEPTIBLE][a] = age_counts[a];
-        c.beds = c.avail_beds = cfg->hospital_beds; c.icu = c.avail_icu = cfg->icu_units;
-        c.p_successful_tracing = 1.0f;
-        c.seed = cfg->seed + (uint32_t)r;
-        u32x4 k = philox(c.seed, 0, 0, PU_PERM, 0);
-        c.fkey[0] = k.x; c.fkey[1] = k.y; c.fkey[2] = k.z; c.fkey[3] = k.w;
-        for (int i = 0; i < RB_MAX_VACC; i++) c.vacc_cursor[i] = -2;
-    }
-    CK(cudaMemcpy(G.ctr, hc.data(), sizeof(RepCtr) * R, cudaMemcpyHostToDevice));
+    e->age_counts.assign(age_counts, age_counts + cfg->n_ages);
+    if (init_counters(e, cfg->seed)) { rb_destroy(e); return 1; }
     CK(cudaMemset(G.stats, 0, sizeof(int32_t) * (size_t)R * (cfg->max_days + 1) * G.row_len));
     CK(cudaMemset(e->d_sched, 0, sizeof(rb_day_params) * ((size_t)cfg->max_days + 1)));
     // launch geometry: grid-stride kernels sized in multiples of the SM count
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     int sms = prop.multiProcessorCount;
-    int want = (G.Npad / 4 + 255) / 256;
+    int want = (G.Npad + SW_TILE - 1) / SW_TILE;
     int per_rep = (sms * 8 + R - 1) / R; if (per_rep < 4) per_rep = 4;
     e->sweep_blocks = want < per_rep ? want : per_rep; if (e->sweep_blocks < 1) e->sweep_blocks = 1;
     e->list_blocks = (sms * 4 + R - 1) / R; if (e->list_blocks < 2) e->list_blocks = 2;
@@ -1036,6 +1093,17 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     *out = e;
+    return 0;
+}
+
+extern "C" int rb_reset(rb_engine *e, uint32_t seed) {
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    e->cfg.seed = seed;
+    e->day = 0;
+    if (init_counters(e, seed)) return 1;
+    k_init<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G); e->launches++;
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -1075,26 +1143,82 @@ extern "C" int rb_set_schedule(rb_engine *e, int32_t day0, int32_t n, const rb_d
     return 0;
 }
 
+// One "segment" = the grid kernels of day d followed by the fused day boundary d -> d+1.
+static void launch_segment(rb_engine *e, cudaStream_t st) {
+    const Eng &G = e->G;
+    k_sweep<<<dim3(e->sweep_blocks, G.R), SW_THREADS, 0, st>>>(G);
+    k_expose<<<dim3(e->list_blocks, G.R), 256, 0, st>>>(G);
+    k_resolve<<<dim3(e->list_blocks, G.R), 256, 0, st>>>(G);
+    k_between<<<G.R, PRE_THREADS, 0, st>>>(G);
+}
+
+// No kernel takes the day as an argument (each replica carries its own day counter and reads the schedule from
+// device memory), so a captured graph of GRAPH_DAYS segments is replayed for any stretch of days.
+#define GRAPH_DAYS 16
+static int build_graphs(rb_engine *e) {
+    for (int which = 0; which < 2; which++) {
+        int nseg = which == 0 ? GRAPH_DAYS : 1;
+        cudaGraph_t g;
+        CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < nseg; i++) launch_segment(e, e->stream);
+        CK(cudaStreamEndCapture(e->stream, &g));
+        CK(cudaGraphInstantiate(&e->graph[which], g, 0));
+        CK(cudaGraphDestroy(g));
+    }
+    e->have_graphs = true;
+    return 0;
+}
+
 extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     CK(cudaSetDevice(e->cfg.device));
+    if (n_days <= 0) return 0;
     if (e->day + n_days > e->cfg.max_days) { snprintf(g_err, sizeof g_err, "max_days exceeded"); return 1; }
     for (int d = 0; d < n_days; d++) {
         int ep = e->h_sched[e->day + d].table_epoch;
         if (ep < 0 || ep >= e->n_table_slots || !e->tables[ep]) { snprintf(g_err, sizeof g_err, "contact table %d not set", ep); return 1; }
     }
+    if (!e->have_graphs && build_graphs(e)) return 1;
     const Eng &G = e->G;
     const int R = G.R;
     CK(cudaEventRecord(e->ev0, e->stream));
-    for (int d = 0; d < n_days; d++) {
-        k_pre<<<R, PRE_THREADS, 0, e->stream>>>(G);
-        k_sweep<<<dim3(e->sweep_blocks, R), 256, 0, e->stream>>>(G);
-        k_expose<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G);
-        k_resolve<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G);
-        k_post<<<R, PRE_THREADS, 0, e->stream>>>(G);
-        e->launches += 5;
-    }
+    k_pre<<<R, PRE_THREADS, 0, e->stream>>>(G); e->launches++;
+    int mid = n_days - 1;
+    while (mid >= GRAPH_DAYS) { CK(cudaGraphLaunch(e->graph[0], e->stream)); mid -= GRAPH_DAYS; e->launches += 4 * GRAPH_DAYS; }
+    while (mid > 0) { CK(cudaGraphLaunch(e->graph[1], e->stream)); mid -= 1; e->launches += 4; }
+    k_sweep<<<dim3(e->sweep_blocks, R), SW_THREADS, 0, e->stream>>>(G);
+    k_expose<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G);
+    k_resolve<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G);
+    k_post<<<R, PRE_THREADS, 0, e->stream>>>(G);
+    e->launches += 4;
     CK(cudaEventRecord(e->ev1, e->stream));
     CK(cudaGetLastError());
+    e->day += n_days;
+    return 0;
+}
+
+extern "C" int rb_step_profiled(rb_engine *e, int32_t n_days, float *ms_per_kernel) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->day + n_days > e->cfg.max_days) { snprintf(g_err, sizeof g_err, "max_days exceeded"); return 1; }
+    const Eng &G = e->G;
+    const int R = G.R;
+    std::vector<cudaEvent_t> ev((size_t)n_days * 6);
+    for (auto &x : ev) CK(cudaEventCreate(&x));
+    for (int d = 0; d < n_days; d++) {
+        cudaEvent_t *v = &ev[(size_t)d * 6];
+        CK(cudaEventRecord(v[0], e->stream));
+        k_pre<<<R, PRE_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[1], e->stream));
+        k_sweep<<<dim3(e->sweep_blocks, R), SW_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[2], e->stream));
+        k_expose<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G); CK(cudaEventRecord(v[3], e->stream));
+        k_resolve<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G); CK(cudaEventRecord(v[4], e->stream));
+        k_post<<<R, PRE_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[5], e->stream));
+        e->launches += 5;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < RB_N_KERNELS; k++) ms_per_kernel[k] = 0;
+    for (int d = 0; d < n_days; d++)
+        for (int k = 0; k < RB_N_KERNELS; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ev[(size_t)d * 6 + k], ev[(size_t)d * 6 + k + 1])); ms_per_kernel[k] += ms; }
+    for (auto &x : ev) cudaEventDestroy(x);
     e->day += n_days;
     return 0;
 }

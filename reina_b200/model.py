@@ -280,8 +280,14 @@ class Context:
         self.start_date = start_date
         self.day = 0
         self.interventions = []
-        self.contact_matrix = ContactMatrix(population_params['contacts_per_day'], n_ages)
+        self._contacts_per_day = ContactMatrix._records(population_params['contacts_per_day'])
+        self._n_variants = len(variants)
+        self._reset_host_state()
+        self._state_day = -1    # day whose stats row is known to be on the device
 
+    def _reset_host_state(self):
+        """Host half of a fresh Context: HealthcareSystem / Population settings and the contact matrix."""
+        self.contact_matrix = ContactMatrix(self._contacts_per_day, self.n_ages)
         # HealthcareSystem host-side settings (main.pyx:461-471)
         self._testing_mode = NO_TESTING
         self._p_detected_anyway = f32(0)
@@ -289,16 +295,16 @@ class Context:
         self._vaccinations = []
         # Population import settings (main.pyx:1366-1369)
         self._weekly_amount = 0
-        self._weekly_leftover = [0.0] * (len(variants) + 1)
-        self._weekly_shares = [0.0] * len(variants)
+        self._weekly_leftover = [0.0] * (self._n_variants + 1)
+        self._weekly_shares = [0.0] * self._n_variants
         self._weekly_shares[0] = 1.0
         # pending one-day effects collected by apply_intervention
         self._pending = dict(beds=0, icu=0, imports=[])
         self._epoch = 0
         self._epoch_mobility = {0: float(1 - self.contact_matrix.mobility_factor)}
-        self._engine.set_contact_table(0, self.contact_matrix.generate())
-        self._sched_to = 0      # days [0, _sched_to) already have their parameters on the device
-        self._state_day = -1    # day whose stats row is known to be on the device
+        self._tables = {0: self.contact_matrix.generate()}
+        self._engine.set_contact_table(0, self._tables[0])
+        self._plan = []         # DayParams of every day planned so far (the schedule does not depend on the seed)
 
     # -- reference surface ------------------------------------------------------------------------
     def get_date_for_today(self):                      # main.pyx:1806-1808
@@ -306,6 +312,12 @@ class Context:
         return (d + timedelta(days=self.day)).isoformat()
 
     def add_intervention(self, iv):                    # main.pyx:1810-1811
+        if len(self._plan) > self.day:
+            # days beyond today were planned ahead (after reset()): re-plan them with the new list
+            done = self.day
+            self._reset_host_state()
+            for _ in range(done):
+                self._plan_next_day()
         self.interventions.append(iv)
 
     def find_variant(self, variant_str):               # main.pyx:1868-1878
@@ -392,9 +404,11 @@ class Context:
         """`days` x iterate() in one device-resident run (the per-day schedule is computed up front)."""
         if self.day + days > self.max_days:
             raise ValueError('max_days=%d exceeded' % self.max_days)
-        params = [self._next_day_params() for _ in range(days)]
-        self._engine.set_schedule(self.day - days, params)
+        while len(self._plan) < self.day + days:
+            self._plan_next_day()
+        self._engine.set_schedule(self.day, self._plan[self.day:self.day + days])
         self._engine.step(days)
+        self.day += days
         self._engine.sync()
         problems = self._engine.problem()
         if problems.any():                              # main.pyx:2017-2018
@@ -413,6 +427,19 @@ class Context:
         names += ['infected_by_variant_%d' % i for i in range(_abi.RB_MAX_VARIANTS)]
         assert len(names) == len(ATTRS) * G + _abi.RB_N_SCALARS
         return names
+
+    def reset(self, random_seed):
+        """A fresh Context(random_seed=...) with the same inputs and interventions, without reallocating
+        device memory.  The planned schedule is kept (it does not depend on the seed)."""
+        self._engine.reset(random_seed)
+        self.day = 0
+        self._state_day = -1
+
+    def upload_inputs(self):
+        """Re-send every contact table to the device (bench.py: per-step host->device input copy)."""
+        for epoch, t in self._tables.items():
+            self._engine.set_contact_table(epoch, t)
+        return sum(sum(a.nbytes for a in t.values()) for t in self._tables.values())
 
     def close(self):
         self._engine.close()
@@ -437,10 +464,10 @@ class Context:
             self._vaccinations.append(v)
         v['nr_daily'] = daily
 
-    def _next_day_params(self):
-        """Host half of one iterate(): interventions dated today (main.pyx:2012-2015), then the settings
-        Population.init_day (:1687-1699) and HealthcareSystem.iterate (:547-558) read.  Advances self.day."""
-        today = self.get_date_for_today()
+    def _plan_next_day(self):
+        """Host half of one iterate(): interventions dated that day (main.pyx:2012-2015), then the settings
+        Population.init_day (:1687-1699) and HealthcareSystem.iterate (:547-558) read.  Appends to the plan."""
+        today = (date.fromisoformat(self.start_date) + timedelta(days=len(self._plan))).isoformat()
         for iv in self.interventions:
             if iv.date == today:
                 self.apply_intervention(iv)
@@ -460,7 +487,8 @@ class Context:
         cm = self.contact_matrix
         if cm.mobility_factor_changed:
             self._epoch += 1
-            self._engine.set_contact_table(self._epoch, cm.generate())
+            self._tables[self._epoch] = cm.generate()
+            self._engine.set_contact_table(self._epoch, self._tables[self._epoch])
             self._epoch_mobility[self._epoch] = float(1 - cm.mobility_factor)
             cm.mobility_factor_changed = False
         dp.table_epoch = self._epoch
@@ -485,7 +513,7 @@ class Context:
             dp.vacc_slot[n] = v['slot']
             n += 1
         dp.n_vacc = n
-        self.day += 1
+        self._plan.append(dp)
         return dp
 
     def _row_to_state(self, row):
