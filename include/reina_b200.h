@@ -25,6 +25,7 @@ extern "C" {
 #define RB_MAX_AGES 128      /* single-year ages 0..n_ages-1 (reference: 101, main.pyx:1355) */
 #define RB_MAX_VARIANTS 4    /* wild-type + configured variants (main.pyx:868-881) */
 #define RB_MAX_ROWS 96       /* contact rows per participant age: 6 places x 15 bands = 90 (main.pyx:1094-1103) */
+#define RB_NCDF 100          /* contacts per infector per day are capped at 100 (get_contacts limit, main.pyx:1539) */
 #define RB_MAX_IMPORT_EVENTS 8
 #define RB_MAX_VACC 8
 #define RB_MAX_IMPORT_CLASSES 16
@@ -132,10 +133,15 @@ int rb_reset(rb_engine *e, uint32_t seed);
 
 /* ContactMatrix.generate_contact_probabilities output (main.pyx:1184-1235) for one mobility epoch:
  * per participant age `n_rows[age]` rows of {cum_p, contact band [lo,hi], place, mask_p}, arrays are
- * [n_ages][RB_MAX_ROWS]; nr_contacts[age] = nr_contacts_by_age (main.pyx:1209-1211). */
+ * [n_ages][RB_MAX_ROWS]; nr_contacts[age] = nr_contacts_by_age (main.pyx:1209-1211).
+ * ncontact_cdf[age][cls][k] = P(number of contacts <= k) for ContactMatrix.get_nr_contacts (main.pyx:1308-1320:
+ * n = min(limit, int(max(1, lognormal(0, 0.5) * nr_contacts_by_age[age] * factor)) - 1)), tabulated by the host in
+ * double precision so that the device draws n with one uniform and a binary search instead of evaluating
+ * exp/log per infector.  cls 0: factor 1, limit 100 (incubating / asymptomatic); cls 1: factor 0.5, limit 5
+ * (symptomatic, Disease.get_exposed_people :945-953).  Array is [n_ages][2][RB_NCDF]. */
 int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *n_rows, const double *cum_p,
                          const int32_t *age_lo, const int32_t *age_hi, const uint8_t *place,
-                         const float *mask_p, const double *nr_contacts);
+                         const float *mask_p, const double *nr_contacts, const double *ncontact_cdf);
 
 /* Host-side schedule for days [day0, day0 + n). */
 int rb_set_schedule(rb_engine *e, int32_t day0, int32_t n, const rb_day_params *params);

@@ -59,6 +59,7 @@ typedef struct {
     uint8_t place[RB_MAX_AGES][RB_MAX_ROWS];
     float mask_p[RB_MAX_AGES][RB_MAX_ROWS];
     double nr_contacts[RB_MAX_AGES];
+    double ncdf[RB_MAX_AGES][2][RB_NCDF];
     int set;
 } Table;
 
@@ -177,14 +178,6 @@ static float gamma_f(uint32_t seed, uint32_t c0, uint32_t c1, uint32_t purpose, 
         float z2 = z * z;
         if (u < 1.0f - 0.0331f * (z2 * z2)) return (d * v) * theta;
         if (rb_logf(u) < 0.5f * z2 + d * ((1.0f - v) + rb_logf(v))) return (d * v) * theta;
-    }
-}
-static float lognormal_half(uint32_t seed, uint32_t c0, uint32_t c1, uint32_t purpose) {  /* lognormal(0, 0.5) */
-    for (uint32_t it = 0;; it++) {
-        uint32_t x[4];
-        philox(seed, KEY1, c0, c1, purpose, it, x);
-        float z;
-        if (polar_normal(x, &z)) return rb_expf(0.5f * z);
     }
 }
 static inline int chance(double u, float p) {   /* RandomPool.chance, simrandom.pyx:32-39 */
@@ -463,36 +456,41 @@ static int person_expose_others(rb_engine *e, Replica *r, int32_t ai) {
     if (p->detected) return 0;
     float si = source_infectiousness(e, p);
     if (si == 0.0f) return 0;
-    float factor = 1.0f; int limit = 100;
-    if (p->state == RB_ILLNESS && p->severity != RB_ASYMPTOMATIC) { factor = 0.5f; limit = 5; }
+    /* get_nr_contacts, main.pyx:1308-1320: one uniform against the tabulated distribution of n */
+    int cls = 0, limit = 100;
+    if (p->state == RB_ILLNESS && p->severity != RB_ASYMPTOMATIC) { cls = 1; limit = 5; }
     const Table *tb = &e->tables[r->epoch];
-    float f = lognormal_half(r->seed, (uint32_t)ai, (uint32_t)e->day, PU_NCONTACT) * (float)tb->nr_contacts[p->age];
-    f = f * factor;
-    if (f < 1.0f) f = 1.0f;
-    int n = (int)f - 1;
-    if (n > limit) n = limit;
-    if (n > MAX_CONTACTS) { r->problem = RB_TOO_MANY_CONTACTS; return 0; }
+    int n;
+    {
+        uint32_t x[4];
+        philox(r->seed, KEY1, (uint32_t)ai, (uint32_t)e->day, PU_NCONTACT, 0, x);
+        double u = u01d(x[0], x[1]);
+        const double *cdf = tb->ncdf[p->age][cls];
+        int lo = 0, hi = limit;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (u < cdf[mid]) hi = mid; else lo = mid + 1; }
+        n = lo;
+    }
     const rb_variant *v = &e->variants[p->variant];
     if (p->severity == RB_ASYMPTOMATIC) si = si * v->p_asymptomatic_infection;
     int nrows = tb->n_rows[p->age];
     for (int slot = 0; slot < n; slot++) {
         uint32_t x[4];
         philox(r->seed, KEY1, (uint32_t)ai, (uint32_t)e->day, PU_CONTACT | ((uint32_t)slot << 8), 0, x);
-        double u = u01d(x[0], x[1]);
+        /* one Philox block per contact: word 0 -> row, 1 -> person within the band, 2 -> transmission, 3 -> mask */
+        double u = (double)x[0] * (1.0 / 4294967296.0);
         int row = nrows - 1;   /* the reference fails with CONTACT_PROBABILITY_FAILURE here (p ~ 1e-15) */
         for (int i = 0; i < nrows; i++) if (u < tb->cum_p[p->age][i]) { row = i; break; }
-        int32_t ti = tb->start[p->age][row] + (int32_t)(x[2] % (uint32_t)tb->size[p->age][row]);
+        int32_t ti = tb->start[p->age][row] + (int32_t)(x[1] % (uint32_t)tb->size[p->age][row]);
         r->daily_contacts[tb->place[p->age][row]] += 1;
         Agent *t = &r->agents[ti];
         if (t->state != RB_SUSCEPTIBLE) continue;       /* person_expose, main.pyx:238-244 */
         float pr = (si * v->tab[RB_T_SUSCEPTIBILITY][t->age]) * v->infectiousness_multiplier;
-        philox(r->seed, KEY1, (uint32_t)ai, (uint32_t)e->day, PU_CONTACT | ((uint32_t)slot << 8), 1, x);
-        if (!chance(u01d(x[0], x[1]), pr)) continue;
+        if (!chance((double)x[2] * (1.0 / 4294967296.0), pr)) continue;
         float mp = tb->mask_p[p->age][row];
         if (mp != 0.0f) {
             float a = mp * v->p_mask_protects_others, b = mp * v->p_mask_protects_wearer;
             float pm = (a + b) - a * b;
-            if (chance(u01d(x[2], x[3]), pm)) continue;
+            if (chance((double)x[3] * (1.0 / 4294967296.0), pm)) continue;
         }
         person_infect(e, r, ti, ai, -1, slot);
         if (p->has_list && p->n_infected >= MAX_INFECTEES) { r->problem = RB_TOO_MANY_INFECTEES; break; }
@@ -688,7 +686,7 @@ void ro_destroy(rb_engine *e) {
 
 int ro_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *n_rows, const double *cum_p,
                          const int32_t *age_lo, const int32_t *age_hi, const uint8_t *place,
-                         const float *mask_p, const double *nr_contacts) {
+                         const float *mask_p, const double *nr_contacts, const double *ncontact_cdf) {
     if (epoch >= e->n_tables) {
         int n = epoch + 8;
         e->tables = (Table *)realloc(e->tables, sizeof(Table) * n);
@@ -699,6 +697,7 @@ int ro_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *n_rows, con
     for (int age = 0; age < e->cfg.n_ages; age++) {
         t->n_rows[age] = n_rows[age];
         t->nr_contacts[age] = nr_contacts[age];
+        memcpy(t->ncdf[age], ncontact_cdf + (size_t)age * 2 * RB_NCDF, sizeof(double) * 2 * RB_NCDF);
         for (int i = 0; i < n_rows[age]; i++) {
             int k = age * RB_MAX_ROWS + i;
             t->cum_p[age][i] = cum_p[k];
@@ -776,10 +775,12 @@ int ro_sample(rb_engine *e, int32_t what, int32_t age, int32_t severity, int32_t
     for (int32_t i = 0; i < n; i++) {
         uint32_t pu = PU_SAMPLE | ((uint32_t)what << 8);
         if (what == 0) {
-            float f = lognormal_half(seed, (uint32_t)i, (uint32_t)age, pu) * (float)e->tables[epoch].nr_contacts[age];
-            if (f < 1.0f) f = 1.0f;
-            int k = (int)f - 1; if (k > 100) k = 100;
-            out[i] = k;
+            uint32_t x[4]; philox(seed, KEY1, (uint32_t)i, (uint32_t)age, pu, 0, x);
+            double u = u01d(x[0], x[1]);
+            const double *cdf = e->tables[epoch].ncdf[age][0];
+            int lo = 0, hi = 100;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (u < cdf[mid]) hi = mid; else lo = mid + 1; }
+            out[i] = lo;
         } else if (what == 1) {
             uint32_t x[4]; philox(seed, KEY1, (uint32_t)i, (uint32_t)age, pu, 0, x);
             out[i] = symptom_severity(v, age, u01f(x[0]), 0);

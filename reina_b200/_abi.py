@@ -12,6 +12,7 @@ import numpy as np
 RB_MAX_AGES = 128
 RB_MAX_VARIANTS = 4
 RB_MAX_ROWS = 96
+RB_NCDF = 100
 RB_MAX_IMPORT_EVENTS = 8
 RB_MAX_VACC = 8
 RB_MAX_IMPORT_CLASSES = 16
@@ -115,7 +116,7 @@ class Library:
         f['set_contact_table'].argtypes = [vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double),
                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                            C.POINTER(C.c_uint8), C.POINTER(C.c_float),
-                                           C.POINTER(C.c_double)]
+                                           C.POINTER(C.c_double), C.POINTER(C.c_double)]
         f['set_schedule'].argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(DayParams)]
         f['step'].argtypes = [vp, C.c_int32]
         f['reset'].argtypes = [vp, C.c_uint32]
@@ -195,7 +196,8 @@ class Engine:
         self.lib.check(f(self.h, epoch, _ptr(t['n_rows'], C.c_int32), _ptr(t['cum_p'], C.c_double),
                          _ptr(t['age_lo'], C.c_int32), _ptr(t['age_hi'], C.c_int32),
                          _ptr(t['place'], C.c_uint8), _ptr(t['mask_p'], C.c_float),
-                         _ptr(t['nr_contacts'], C.c_double)), 'set_contact_table')
+                         _ptr(t['nr_contacts'], C.c_double), _ptr(t['ncontact_cdf'], C.c_double)),
+                       'set_contact_table')
 
     def set_schedule(self, day0, params):
         arr = (DayParams * len(params))(*params)

@@ -63,11 +63,15 @@ enum { EV_HOSP_CLAIM = 0, EV_WARD_RELEASE = 1, EV_TO_ICU = 2, EV_ICU_RELEASE = 3
 struct DevTable {
     int32_t n_rows[RB_MAX_AGES];
     float nr_contacts[RB_MAX_AGES];
+    double ncdf[RB_MAX_AGES][2][RB_NCDF];
     double cum_p[RB_MAX_AGES][RB_MAX_ROWS];
     int32_t start[RB_MAX_AGES][RB_MAX_ROWS];
     int32_t size[RB_MAX_AGES][RB_MAX_ROWS];
     float mask_p[RB_MAX_AGES][RB_MAX_ROWS];
     uint8_t place[RB_MAX_AGES][RB_MAX_ROWS];
+    uint8_t lo_age[RB_MAX_AGES][RB_MAX_ROWS], hi_age[RB_MAX_AGES][RB_MAX_ROWS];
+    uint8_t susc_uniform[RB_MAX_AGES][RB_MAX_ROWS];   // susceptibility identical for every age of the row's band
+    uint8_t guide[RB_MAX_AGES][256];                  // first row whose cum_p exceeds b/256: start of the row search
 };
 
 struct Attempt { uint32_t cand, parent; unsigned long long key; };
@@ -95,6 +99,8 @@ struct Eng {
     int32_t *infector, *first_child, *next_sib;
     int16_t *vacc_day;
     unsigned long long *winner;
+    uint32_t *sus;                                 // [R][sus_words] 1 bit per agent: still SUSCEPTIBLE (L2-resident gather target)
+    int32_t sus_words;
     uint2 *items;
     Attempt *succ;
     unsigned long long *ev_key; int32_t *ev_agent;
@@ -112,6 +118,11 @@ struct Eng {
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ int age_of(const Eng &G, int32_t a) {
     int lo = 0, hi = G.n_ages;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(&G.age_start[mid]) <= a) lo = mid; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ int age_in_band(const Eng &G, int32_t a, int lo, int hi) {   // age of agent a, known to lie in [lo, hi]
+    hi += 1;
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(&G.age_start[mid]) <= a) lo = mid; else hi = mid; }
     return lo;
 }
@@ -167,6 +178,7 @@ __device__ void device_infect(const Eng &G, int r, RepCtr *c, int32_t t, int32_t
     if (fresh) nh |= H_FRESH;
     if (c->testing_mode == RB_ALL_WITH_SYMPTOMS_CT) nh |= H_LIST;
     G.hot[base + t] = nh;
+    atomicAnd(&G.sus[(size_t)r * G.sus_words + (t >> 5)], ~(1u << (t & 31)));
     count_add(c, RB_A_SUSCEPTIBLE, age, -1);
     count_add(c, RB_A_INFECTED, age, 1);
     count_add(c, RB_A_ALL_INFECTED, age, 1);
@@ -543,15 +555,15 @@ __device__ __forceinline__ uint32_t advance_agent(const Eng &G, int r, RepCtr *c
         // get_exposed_people / get_nr_contacts, main.pyx:936-955, 1308-1320
         int dayidx = st == RB_INCUBATION ? -(int)H_DL(h) : (int)H_DOI(h);
         if (!(h & H_DET) && dayidx >= -10 && dayidx <= 10 && v->iot[dayidx + 10] != 0.0f) {
-            float factor = 1.0f; int limit = 100;
-            if (st == RB_ILLNESS && sev != RB_ASYMPTOMATIC) { factor = 0.5f; limit = 5; }
-            float f = lognormal_half(c->seed, (uint32_t)a, (uint32_t)day, PU_NCONTACT) * tb->nr_contacts[age];
-            f = f * factor;
-            if (f < 1.0f) f = 1.0f;
-            int k = (int)f - 1;
-            if (k > limit) k = limit;
-            if (k > MAX_CONTACTS) { set_problem(c, RB_TOO_MANY_CONTACTS); k = 0; }
-            n = (uint32_t)k;
+            // get_nr_contacts, main.pyx:1308-1320: one uniform against the host-tabulated distribution of n
+            int cls = 0, limit = 100;
+            if (st == RB_ILLNESS && sev != RB_ASYMPTOMATIC) { cls = 1; limit = 5; }
+            u32x4 x = philox(c->seed, (uint32_t)a, (uint32_t)day, PU_NCONTACT, 0);
+            double u = u01d(x.x, x.y);
+            const double *cdf = tb->ncdf[age][cls];
+            int lo = 0, hi = limit;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (u < __ldg(&cdf[mid])) hi = mid; else lo = mid + 1; }
+            n = (uint32_t)lo;
             desc = ((uint32_t)age << 7) | ((uint32_t)(dayidx + 10) << 14) | ((sev == RB_ASYMPTOMATIC ? 1u : 0u) << 19) | (var << 20);
         }
     }
@@ -645,83 +657,96 @@ __device__ __forceinline__ uint32_t advance_agent(const Eng &G, int r, RepCtr *c
     return n;
 }
 
-// The daily sweep streams the packed words tile by tile (coalesced 16-byte loads), compacts the few agents that
-// have anything to do today into shared memory, and only then runs the state machine on the compacted list, so the
-// branchy part executes with full warps.  Contact work items are allocated with one block-level prefix sum and one
-// atomic per tile and written cooperatively (coalesced).
+// The daily sweep.  Every warp streams its share of the packed words (coalesced 16-byte loads, 256 agents per
+// step), pushes the few agents that have anything to do today into a private shared-memory ring, and runs the state
+// machine only on full batches of 32 queued agents -- so the branchy part executes on dense warps, there is no
+// block-level barrier anywhere, and other warps keep the memory pipe busy meanwhile.  Contact work items are
+// allocated with a warp prefix sum and one atomic per batch and written cooperatively (coalesced).
 #define SW_THREADS 256
-#define SW_TILE 2048
+#define SW_WARPS (SW_THREADS / 32)
+#define SW_CHUNK 256
+#define SW_QCAP 512
+__device__ __forceinline__ void sweep_batch(const Eng &G, int r, RepCtr *c, const DevTable *tb, const uint32_t *qi, const uint32_t *qw,
+                                            uint32_t head, uint32_t m, uint2 *items, int lane) {
+    const size_t base = (size_t)r * G.Npad;
+    uint32_t cnt = 0, desc = 0, a = 0;
+    if ((uint32_t)lane < m) {
+        a = qi[(head + lane) & (SW_QCAP - 1)];
+        uint32_t h = qw[(head + lane) & (SW_QCAP - 1)];
+        bool dirty = false;
+        cnt = advance_agent(G, r, c, tb, (int32_t)a, h, dirty, desc);
+        if (dirty) G.hot[base + a] = h;
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
+    if (wtot == 0) return;
+    const uint32_t excl = incl - cnt;
+    uint32_t gbase = 0;
+    if (lane == 31) { gbase = atomicAdd(&c->n_items, wtot); atomicAdd(&c->exposed_per_day, (int)wtot); }
+    gbase = __shfl_sync(0xffffffffu, gbase, 31);
+    if (gbase + wtot > G.cap_items) { if (lane == 0) set_problem(c, RB_OTHER_FAILURE); return; }
+    for (uint32_t t0 = 0; t0 < wtot; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        // owner = largest lane whose exclusive prefix is <= t (lanes with zero contacts share a prefix with their successor)
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            uint32_t e = __shfl_sync(0xffffffffu, excl, (lo + step) & 31);
+            if (lo + step < 32 && e <= t) lo += step;
+        }
+        const uint32_t oa = __shfl_sync(0xffffffffu, a, lo), od = __shfl_sync(0xffffffffu, desc, lo), oe = __shfl_sync(0xffffffffu, excl, lo);
+        if (t < wtot) items[gbase + t] = make_uint2(oa, od | (t - oe));
+    }
+}
+
 __global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
-    __shared__ uint32_t s_idx[SW_TILE];     // tile-local index of each active agent
-    __shared__ uint32_t s_word[SW_TILE];    // its packed word; later the exclusive prefix of contact counts
-    __shared__ uint32_t s_desc[SW_TILE];    // contact descriptor (age, infectiousness day, asymptomatic, variant)
-    __shared__ int warp_sums[32];
-    __shared__ uint32_t s_n[3];             // rotating counters: reset two iterations ahead, between barriers
-    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_qi[SW_WARPS][SW_QCAP];   // queued agent index
+    __shared__ uint32_t s_qw[SW_WARPS][SW_QCAP];   // its packed word
     const int r = blockIdx.y;
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
     const DevTable *tb = G.tables[c->epoch];
     const uint4 *hot4 = reinterpret_cast<const uint4 *>(G.hot + base);
     uint2 *items = G.items + (size_t)r * G.cap_items;
-    const int tid = threadIdx.x;
-    const int n_tiles = (G.Npad + SW_TILE - 1) / SW_TILE;
-    if (tid < 3) s_n[tid] = 0;
-    __syncthreads();
-    int par = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par = par == 2 ? 0 : par + 1) {
-        const int t0 = tile * SW_TILE;
-        // phase 1: stream + compact
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *qi = s_qi[warp], *qw = s_qw[warp];
+    const int n_chunks = (G.Npad + SW_CHUNK - 1) / SW_CHUNK;
+    const int n4 = G.Npad >> 2;
+    uint32_t head = 0, tail = 0;
+    for (int chunk = blockIdx.x * SW_WARPS + warp; chunk < n_chunks; chunk += gridDim.x * SW_WARPS) {
+        const int a0 = chunk * SW_CHUNK;
+        const int i0 = (a0 >> 2) + lane, i1 = i0 + 32;
+        uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
+        if (i0 < n4) w0 = __ldg(&hot4[i0]);
+        if (i1 < n4) w1 = __ldg(&hot4[i1]);
+        const uint32_t hw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        uint32_t act = 0;
 #pragma unroll
-        for (int q = 0; q < SW_TILE / (SW_THREADS * 4); q++) {
-            int li = q * SW_THREADS * 4 + tid * 4;
-            if (t0 + li < G.Npad) {
-                uint4 w = __ldg(&hot4[(t0 + li) >> 2]);
-                uint32_t hw[4] = {w.x, w.y, w.z, w.w};
+        for (int j = 0; j < 8; j++) {
+            uint32_t st = H_STATE(hw[j]);
+            if (st != RB_SUSCEPTIBLE && !(st >= RB_RECOVERED && (hw[j] & H_INCL))) act |= 1u << j;
+        }
+        if (!__any_sync(0xffffffffu, act != 0)) continue;
+        uint32_t mine = __popc(act), incl = mine;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    uint32_t st = H_STATE(hw[j]);
-                    if (st != RB_SUSCEPTIBLE && !(st >= RB_RECOVERED && (hw[j] & H_INCL))) {
-                        uint32_t p = atomicAdd(&s_n[par], 1u);
-                        s_idx[p] = (uint32_t)(li + j); s_word[p] = hw[j];
-                    }
-                }
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t p = tail + incl - mine;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (act & (1u << j)) {
+                qi[p & (SW_QCAP - 1)] = (uint32_t)(a0 + (j < 4 ? lane * 4 + j : 128 + lane * 4 + (j - 4)));
+                qw[p & (SW_QCAP - 1)] = hw[j];
+                p++;
             }
-        }
-        __syncthreads();
-        const uint32_t n = s_n[par];
-        if (tid == 0) s_n[par == 0 ? 2 : par - 1] = 0;      // (i + 2) % 3: last read before this barrier, next used after the next one
-        if (n == 0) continue;
-        // phase 2: state machine on the compacted list (thread k owns entries k*per .. so that the scan is local)
-        const uint32_t per = (n + SW_THREADS - 1) / SW_THREADS;
-        const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
-        uint32_t mine = 0;
-        for (uint32_t k = lo; k < hi; k++) {
-            int32_t a = t0 + (int32_t)s_idx[k];
-            uint32_t h = s_word[k], desc = 0; bool dirty = false;
-            uint32_t cnt = advance_agent(G, r, c, tb, a, h, dirty, desc);
-            if (dirty) G.hot[base + a] = h;
-            s_desc[k] = desc;
-            s_word[k] = cnt;
-            mine += cnt;
-        }
-        int total;
-        int incl = block_scan_incl((int)mine, &total, warp_sums);
-        if (total == 0) { __syncthreads(); continue; }
-        uint32_t run = (uint32_t)incl - mine;
-        for (uint32_t k = lo; k < hi; k++) { uint32_t cnt = s_word[k]; s_word[k] = run; run += cnt; }
-        if (tid == 0) { s_base = atomicAdd(&c->n_items, (uint32_t)total); atomicAdd(&c->exposed_per_day, total); }
-        __syncthreads();
-        const uint32_t gbase = s_base;
-        if (gbase + (uint32_t)total > G.cap_items) { if (tid == 0) set_problem(c, RB_OTHER_FAILURE); __syncthreads(); continue; }
-        // phase 3: one work item per contact slot, written cooperatively
-        for (uint32_t t = tid; t < (uint32_t)total; t += SW_THREADS) {
-            uint32_t a0 = 0, b0 = n;                  // largest k with prefix[k] <= t
-            while (b0 - a0 > 1) { uint32_t mid = (a0 + b0) >> 1; if (s_word[mid] <= t) a0 = mid; else b0 = mid; }
-            items[gbase + t] = make_uint2((uint32_t)t0 + s_idx[a0], s_desc[a0] | (t - s_word[a0]));
-        }
-        __syncthreads();
+        tail += tot;
+        __syncwarp();
+        while (tail - head >= 32) { sweep_batch(G, r, c, tb, qi, qw, head, 32, items, lane); head += 32; }
+        __syncwarp();
     }
+    if (tail != head) sweep_batch(G, r, c, tb, qi, qw, head, tail - head, items, lane);
 }
 
 // ---------------------------------------------------------------- k_expose
@@ -739,33 +764,38 @@ __global__ void __launch_bounds__(256) k_expose(Eng G) {
     __syncthreads();
     const uint2 *items = G.items + (size_t)r * G.cap_items;
     Attempt *succ = G.succ + (size_t)r * G.cap_succ;
+    const uint32_t *sus = G.sus + (size_t)r * G.sus_words;
     const uint32_t day = (uint32_t)c->day;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint2 it = items[i];
         uint32_t a = it.x, slot = it.y & 127u, age = (it.y >> 7) & 127u, dayidx = (it.y >> 14) & 31u;
         bool asym = (it.y >> 19) & 1u; uint32_t var = (it.y >> 20) & 3u;
+        // one Philox block per contact: word x -> row, y -> person within the band, z -> transmission, w -> mask
         u32x4 x = philox(c->seed, a, day, PU_CONTACT | (slot << 8), 0);
-        double u = u01d(x.x, x.y);
-        int nrows = tb->n_rows[age];
+        const double u = (double)x.x * (1.0 / 4294967296.0);
+        const int nrows = tb->n_rows[age];
         const double *cum = tb->cum_p[age];
-        int lo = 0, hi = nrows;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (u < cum[mid]) hi = mid; else lo = mid + 1; }
-        int row = lo < nrows ? lo : nrows - 1;      // the reference fails here with CONTACT_PROBABILITY_FAILURE (p ~ 1e-15)
-        uint32_t t = (uint32_t)tb->start[age][row] + x.z % (uint32_t)tb->size[age][row];
+        // get_one_contact (main.pyx:1290-1304) is a linear scan for the first row with u < cum_p; rows below
+        // guide[u's top byte] cannot match, so the scan starts there and ends after ~1 step
+        int row = tb->guide[age][x.x >> 24];
+        while (row < nrows - 1 && !(u < cum[row])) row++;      // last row on overrun: the reference fails there (p ~ 1e-15)
+        uint32_t t = (uint32_t)tb->start[age][row] + x.y % (uint32_t)tb->size[age][row];
         atomicAdd(&s_place[tb->place[age][row]], 1);
-        uint32_t ht = G.hot[base + t];
-        if (H_STATE(ht) != RB_SUSCEPTIBLE) continue;
+        // person_expose (main.pyx:238-244): only a SUSCEPTIBLE target can be infected; the 1-bit-per-agent map
+        // keeps this random gather inside L2 instead of pulling a 32-byte DRAM sector per contact
+        if (!((__ldg(&sus[t >> 5]) >> (t & 31)) & 1u)) continue;
         const rb_variant *v = &G.variants[var];
         float si = v->iot[dayidx];
         if (asym) si = si * v->p_asymptomatic_infection;
-        float pr = (si * v->tab[RB_T_SUSCEPTIBILITY][age_of(G, (int32_t)t)]) * v->infectiousness_multiplier;
-        u32x4 y = philox(c->seed, a, day, PU_CONTACT | (slot << 8), 1);
-        if (!chance(u01d(y.x, y.y), pr)) continue;
+        int tage = tb->susc_uniform[age][row] ? (int)tb->lo_age[age][row]
+                                              : age_in_band(G, (int32_t)t, tb->lo_age[age][row], tb->hi_age[age][row]);
+        float pr = (si * v->tab[RB_T_SUSCEPTIBILITY][tage]) * v->infectiousness_multiplier;
+        if (!chance((double)x.z * (1.0 / 4294967296.0), pr)) continue;
         float mp = tb->mask_p[age][row];
         if (mp != 0.0f) {
             float ma = mp * v->p_mask_protects_others, mb = mp * v->p_mask_protects_wearer;
             float pm = (ma + mb) - ma * mb;
-            if (chance(u01d(y.z, y.w), pm)) continue;
+            if (chance((double)x.w * (1.0 / 4294967296.0), pm)) continue;
         }
         unsigned long long key = ((unsigned long long)sweep_pos(G, c, a) << 7) | slot;
         uint32_t idx = atomicAdd(&c->n_succ, 1u);
@@ -913,6 +943,11 @@ __global__ void k_init(Eng G) {
         G.infector[base + i] = -1; G.first_child[base + i] = -1; G.next_sib[base + i] = -1;
         G.vacc_day[base + i] = -1; G.winner[base + i] = KEY_IDLE;
     }
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < G.sus_words; w += gridDim.x * blockDim.x) {
+        int first = w * 32;
+        uint32_t m = first + 32 <= G.N ? 0xffffffffu : (first >= G.N ? 0u : ((1u << (G.N - first)) - 1u));
+        G.sus[(size_t)r * G.sus_words + w] = m;
+    }
 }
 
 __global__ void k_snapshot(Eng G) {
@@ -928,10 +963,12 @@ __global__ void k_sample(Eng G, int what, int age, int severity, int n, int epoc
         uint32_t pu = PU_SAMPLE | ((uint32_t)what << 8);
         int res;
         if (what == 0) {
-            float f = lognormal_half(seed, (uint32_t)i, (uint32_t)age, pu) * G.tables[epoch]->nr_contacts[age];
-            if (f < 1.0f) f = 1.0f;
-            int k = (int)f - 1; if (k > 100) k = 100;
-            res = k;
+            u32x4 x = philox(seed, (uint32_t)i, (uint32_t)age, pu, 0);
+            double u = u01d(x.x, x.y);
+            const double *cdf = G.tables[epoch]->ncdf[age][0];
+            int lo = 0, hi = 100;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (u < cdf[mid]) hi = mid; else lo = mid + 1; }
+            res = lo;
         } else if (what == 1) {
             u32x4 x = philox(seed, (uint32_t)i, (uint32_t)age, pu, 0);
             res = symptom_severity(v, age, u01f(x.x), false);
@@ -967,6 +1004,7 @@ struct rb_engine {
     rb_day_params *d_sched;
     std::vector<rb_day_params> h_sched;
     std::vector<int32_t> age_start, age_counts;
+    std::vector<rb_variant> h_variants;
     int32_t day;
     float last_ms;
     int64_t launches;
@@ -1053,9 +1091,10 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     G.cap_events = pow2_at_least((uint64_t)N / 16 + 2048);
     G.cap_queue = pow2_at_least((uint64_t)N / 8 + 2048);
     const size_t RN = (size_t)R * G.Npad;
+    G.sus_words = (G.Npad + 31) / 32 + 32;
     if (dalloc(e, &G.hot, RN) || dalloc(e, &G.cold, RN) || dalloc(e, &G.inf_key, RN) || dalloc(e, &G.infector, RN) ||
         dalloc(e, &G.first_child, RN) || dalloc(e, &G.next_sib, RN) || dalloc(e, &G.vacc_day, RN) || dalloc(e, &G.winner, RN) ||
-        dalloc(e, &G.items, (size_t)R * G.cap_items) || dalloc(e, &G.succ, (size_t)R * G.cap_succ) ||
+        dalloc(e, &G.sus, (size_t)R * ((G.Npad + 31) / 32 + 32)) || dalloc(e, &G.items, (size_t)R * G.cap_items) || dalloc(e, &G.succ, (size_t)R * G.cap_succ) ||
         dalloc(e, &G.ev_key, (size_t)R * G.cap_events) || dalloc(e, &G.ev_agent, (size_t)R * G.cap_events) ||
         dalloc(e, &G.q_key, (size_t)R * 2 * G.cap_queue) || dalloc(e, &G.q_agent, (size_t)R * 2 * G.cap_queue) ||
         dalloc(e, &G.ctr, (size_t)R) || dalloc(e, &G.stats, (size_t)R * (cfg->max_days + 1) * G.row_len) ||
@@ -1071,6 +1110,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     if (dalloc(e, &dv, (size_t)cfg->n_variants) || dalloc(e, &d_as, (size_t)cfg->n_ages + 1) || dalloc(e, &d_ga, (size_t)cfg->n_ages) ||
         dalloc(e, &d_ilo, (size_t)RB_MAX_IMPORT_CLASSES) || dalloc(e, &d_ihi, (size_t)RB_MAX_IMPORT_CLASSES) ||
         dalloc(e, &d_icum, (size_t)RB_MAX_IMPORT_CLASSES)) { rb_destroy(e); return 1; }
+    e->h_variants.assign(variants, variants + cfg->n_variants);
     CK(cudaMemcpy(dv, variants, sizeof(rb_variant) * cfg->n_variants, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_as, e->age_start.data(), sizeof(int32_t) * (cfg->n_ages + 1), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_ga, group_of_age, sizeof(int32_t) * cfg->n_ages, cudaMemcpyHostToDevice));
@@ -1085,7 +1125,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     // launch geometry: grid-stride kernels sized in multiples of the SM count
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     int sms = prop.multiProcessorCount;
-    int want = (G.Npad + SW_TILE - 1) / SW_TILE;
+    int want = (G.Npad + SW_CHUNK * SW_WARPS - 1) / (SW_CHUNK * SW_WARPS);
     int per_rep = (sms * 8 + R - 1) / R; if (per_rep < 4) per_rep = 4;
     e->sweep_blocks = want < per_rep ? want : per_rep; if (e->sweep_blocks < 1) e->sweep_blocks = 1;
     e->list_blocks = (sms * 4 + R - 1) / R; if (e->list_blocks < 2) e->list_blocks = 2;
@@ -1109,7 +1149,7 @@ extern "C" int rb_reset(rb_engine *e, uint32_t seed) {
 
 extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *n_rows, const double *cum_p,
                                     const int32_t *age_lo, const int32_t *age_hi, const uint8_t *place,
-                                    const float *mask_p, const double *nr_contacts) {
+                                    const float *mask_p, const double *nr_contacts, const double *ncontact_cdf) {
     if (epoch < 0 || epoch >= e->n_table_slots) { snprintf(g_err, sizeof g_err, "table epoch out of range"); return 1; }
     CK(cudaSetDevice(e->cfg.device));
     DevTable *h = new DevTable();
@@ -1117,15 +1157,28 @@ extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *
     for (int age = 0; age < e->cfg.n_ages; age++) {
         h->n_rows[age] = n_rows[age];
         h->nr_contacts[age] = (float)nr_contacts[age];
+        memcpy(h->ncdf[age], ncontact_cdf + (size_t)age * 2 * RB_NCDF, sizeof(double) * 2 * RB_NCDF);
         for (int i = 0; i < n_rows[age]; i++) {
             int k = age * RB_MAX_ROWS + i;
             h->cum_p[age][i] = cum_p[k];
             h->start[age][i] = e->age_start[age_lo[k]];
             h->size[age][i] = e->age_start[age_hi[k] + 1] - e->age_start[age_lo[k]];
             h->place[age][i] = place[k];
+            h->lo_age[age][i] = (uint8_t)age_lo[k]; h->hi_age[age][i] = (uint8_t)age_hi[k];
+            bool uni = true;
+            for (int v = 0; v < e->cfg.n_variants; v++)
+                for (int g = age_lo[k]; g <= age_hi[k]; g++)
+                    if (e->h_variants[v].tab[RB_T_SUSCEPTIBILITY][g] != e->h_variants[v].tab[RB_T_SUSCEPTIBILITY][age_lo[k]]) uni = false;
+            h->susc_uniform[age][i] = uni ? 1 : 0;
             h->mask_p[age][i] = mask_p[k];
         }
     }
+    for (int age = 0; age < e->cfg.n_ages; age++)
+        for (int b = 0; b < 256; b++) {
+            int i = 0;
+            while (i < n_rows[age] - 1 && !(h->cum_p[age][i] > (double)b / 256.0)) i++;
+            h->guide[age][b] = (uint8_t)i;
+        }
     DevTable *d = e->tables[epoch];
     if (!d) { if (dalloc(e, &d, 1)) { delete h; return 1; } e->tables[epoch] = d; }
     CK(cudaStreamSynchronize(e->stream));

@@ -17,6 +17,7 @@ Extensions beyond the reference surface (all optional keyword arguments / extra 
   * `n_replicas=R`: R ensemble members (seeds random_seed .. random_seed+R-1) advanced by the same kernel
     launches; `generate_state(replica=r)`, `run(days)`, `series()`.
 """
+import math
 from datetime import date, timedelta
 
 import numpy as np
@@ -209,7 +210,28 @@ class ContactMatrix:
         t['age_hi'][:, :nk] = np.minimum(self.row_hi, n_ages - 1)
         t['place'][:, :nk] = self.row_place
         t['mask_p'][:, :nk] = self.mask_probabilities[:, self.row_place].astype(np.float32)
+        t['ncontact_cdf'] = ncontact_cdf(total)
         return t
+
+
+def ncontact_cdf(nr_contacts_by_age):
+    """Distribution of ContactMatrix.get_nr_contacts (main.pyx:1308-1320), tabulated.
+
+    n = min(limit, int(max(1, L * c * factor)) - 1) with L ~ lognormal(0, 0.5), c = nr_contacts_by_age[age]:
+    n <= k  <=>  L * c * factor < k + 2  <=>  z < 2 ln((k + 2) / (c * factor)), z standard normal, hence
+    P(n <= k) = Phi(2 ln((k + 2) / (c * factor))).  Class 0: factor 1, limit 100; class 1: factor 0.5, limit 5
+    (Disease.get_exposed_people, main.pyx:945-953).  Returns float64 [n_ages, 2, RB_NCDF]."""
+    n_ages = len(nr_contacts_by_age)
+    out = np.ones((n_ages, 2, _abi.RB_NCDF), dtype=np.float64)
+    for age in range(n_ages):
+        for cls, (factor, limit) in enumerate(((1.0, 100), (0.5, 5))):
+            c = float(nr_contacts_by_age[age]) * factor
+            if not c > 0:
+                continue
+            for k in range(limit):
+                x = 2.0 * math.log((k + 2) / c)
+                out[age, cls, k] = 0.5 * (1.0 + math.erf(x / math.sqrt(2.0)))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
