@@ -528,154 +528,52 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
 }
 
 // ---------------------------------------------------------------- k_sweep
-struct SweepOut { uint32_t n; uint32_t desc; };
-
-// _process_person + person_advance (main.pyx:1968-1979, 395-438) for one agent word.  Returns the number of
-// contacts to sample (person_expose_others :247-281 runs in k_expose) and whether the word changed.
-__device__ __forceinline__ uint32_t advance_agent(const Eng &G, int r, RepCtr *c, const DevTable *tb, int32_t a, uint32_t &h, bool &dirty, uint32_t &desc) {
-    const size_t base = (size_t)r * G.Npad;
-    uint32_t st = H_STATE(h);
-    if (st >= RB_RECOVERED) {
-        if (!(h & H_INCL)) {           // R bookkeeping, main.pyx:1969-1972
-            atomicAdd(&c->total_infectors, 1);
-            atomicAdd(&c->total_infections, (int)(G.cold[base + a] & 0xffffu));
-            h |= H_INCL; dirty = true;
-        }
-        return 0;
-    }
-    if (st == RB_SUSCEPTIBLE) return 0;
-    if (h & H_FRESH) { h &= ~H_FRESH; dirty = true; return 0; }   // infected today before the sweep, main.pyx:402-403
-    dirty = true;
-    const int day = c->day;
-    const int age = age_of(G, a);
-    const uint32_t sev = H_SEV(h), var = H_VAR(h);
-    const rb_variant *v = &G.variants[var];
-    uint32_t n = 0;
-    if (st == RB_INCUBATION || st == RB_ILLNESS) {
-        // get_exposed_people / get_nr_contacts, main.pyx:936-955, 1308-1320
-        int dayidx = st == RB_INCUBATION ? -(int)H_DL(h) : (int)H_DOI(h);
-        if (!(h & H_DET) && dayidx >= -10 && dayidx <= 10 && v->iot[dayidx + 10] != 0.0f) {
-            // get_nr_contacts, main.pyx:1308-1320: one uniform against the host-tabulated distribution of n
-            int cls = 0, limit = 100;
-            if (st == RB_ILLNESS && sev != RB_ASYMPTOMATIC) { cls = 1; limit = 5; }
-            u32x4 x = philox(c->seed, (uint32_t)a, (uint32_t)day, PU_NCONTACT, 0);
-            double u = u01d(x.x, x.y);
-            const double *cdf = tb->ncdf[age][cls];
-            int lo = 0, hi = limit;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (u < __ldg(&cdf[mid])) hi = mid; else lo = mid + 1; }
-            n = (uint32_t)lo;
-            desc = ((uint32_t)age << 7) | ((uint32_t)(dayidx + 10) << 14) | ((sev == RB_ASYMPTOMATIC ? 1u : 0u) << 19) | (var << 20);
-        }
-    }
-    uint32_t dl = H_DL(h);
-    if (st == RB_INCUBATION) {
-        if (dl > 0) dl--;
-        if (dl == 0) {
-            // person_become_ill, main.pyx:284-291; durations :989-1039 fixed from the one onset-to-removed draw
-            float T = (sev == RB_FATAL)
-                ? gamma_f(c->seed, (uint32_t)a, (uint32_t)day, PU_ONSET, v->onset_death_kappa, v->onset_death_theta)
-                : gamma_f(c->seed, (uint32_t)a, (uint32_t)day, PU_ONSET, v->onset_recovery_kappa, v->onset_recovery_theta);
-            float f = T;
-            if (sev != RB_ASYMPTOMATIC && sev != RB_MILD) f = f * v->ratio_before_hospitalisation;
-            dl = (uint32_t)clamp255(round_to_int(f));
-            float w = 0.0f, u = 0.0f;
-            if (sev == RB_SEVERE) w = T * (1.0f - v->ratio_before_hospitalisation);
-            else if (sev == RB_CRITICAL || sev == RB_FATAL) {
-                w = T * v->ratio_in_ward;
-                u = ((1.0f - v->ratio_in_ward) - v->ratio_before_hospitalisation) * T;
-            }
-            uint32_t wd = (uint32_t)clamp255(round_to_int(w)), ud = (uint32_t)clamp255(round_to_int(u));
-            atomicOr(&G.cold[base + a], (wd << 16) | (ud << 24));
-            h = H_SET_STATE(h, RB_ILLNESS);
-            if (sev != RB_ASYMPTOMATIC && !(h & H_DET)) {
-                // seek_testing, main.pyx:595-615
-                bool q = false;
-                int mode = c->testing_mode;
-                if (mode == RB_ALL_WITH_SYMPTOMS || mode == RB_ALL_WITH_SYMPTOMS_CT) q = true;
-                else if (mode == RB_ONLY_SEVERE_SYMPTOMS) {
-                    if (sev >= RB_SEVERE) q = true;
-                    else {
-                        u32x4 x = philox(c->seed, (uint32_t)a, (uint32_t)day, PU_SEEK, 0);
-                        q = chance(u01d(x.x, x.y), c->p_detected_anyway);
-                    }
-                }
-                if (q && !(h & H_QUEUED)) {     // queue_for_testing guards (not DEAD / detected / queued), main.pyx:476
-                    h |= H_QUEUED;
-                    uint32_t idx = atomicAdd(&c->n_newq, 1u);
-                    if (idx < G.cap_queue) {
-                        size_t qb = ((size_t)r * 2 + (c->qsel ^ 1u)) * G.cap_queue;
-                        G.q_key[qb + idx] = QKEY_SWEEP | sweep_pos(G, c, (uint32_t)a);
-                        G.q_agent[qb + idx] = a;
-                    } else set_problem(c, RB_OTHER_FAILURE);
-                }
-            }
-        }
-        h = H_SET_DL(h, dl);
-    } else if (st == RB_ILLNESS) {
-        uint32_t doi = H_DOI(h);
-        if (doi < 31) doi++;
-        h = H_SET_DOI(h, doi);
-        if (dl > 0) dl--;
-        h = H_SET_DL(h, dl);
-        if (dl == 0) {
-            if (sev == RB_FATAL) {                       // person_die, main.pyx:370-374, 1618-1623
-                h = H_SET_STATE(h, RB_DEAD) & ~H_LIST;
-                count_add(c, RB_A_INFECTED, age, -1); count_add(c, RB_A_DEAD, age, 1); count_add(c, RB_A_NON_HOSPITAL_DEATHS, age, 1);
-            } else if (sev >= RB_SEVERE) {               // person_hospitalize, main.pyx:321-338: the bed claim is an event
-                if (!(h & H_DET)) { h |= H_DET; count_add(c, RB_A_DETECTED, age, 1); count_add(c, RB_A_ALL_DETECTED, age, 1); }
-                uint32_t idx = atomicAdd(&c->n_events, 1u);
-                if (idx < G.cap_events) {
-                    G.ev_key[(size_t)r * G.cap_events + idx] = ((unsigned long long)sweep_pos(G, c, (uint32_t)a) << 2) | EV_HOSP_CLAIM;
-                    G.ev_agent[(size_t)r * G.cap_events + idx] = a;
-                } else set_problem(c, RB_OTHER_FAILURE);
-            } else {                                     // person_recover, main.pyx:315-318
-                h = H_SET_STATE(h, RB_RECOVERED) & ~H_LIST;
-                count_add(c, RB_A_INFECTED, age, -1); count_add(c, RB_A_RECOVERED, age, 1);
-            }
-        }
-    } else {   // HOSPITALIZED / IN_ICU
-        if (dl > 0) dl--;
-        h = H_SET_DL(h, dl);
-        if (dl == 0) {
-            int type;
-            if (st == RB_HOSPITALIZED && (sev == RB_CRITICAL || sev == RB_FATAL)) type = EV_TO_ICU;   // main.pyx:430-431
-            else {
-                // person_release_from_hospital, main.pyx:354-367: outcome does not depend on capacity
-                type = st == RB_IN_ICU ? EV_ICU_RELEASE : EV_WARD_RELEASE;
-                count_add(c, st == RB_IN_ICU ? RB_A_IN_ICU : RB_A_IN_WARD, age, -1);
-                count_add(c, RB_A_INFECTED, age, -1);
-                if (sev == RB_FATAL) { h = H_SET_STATE(h, RB_DEAD) & ~H_LIST; count_add(c, RB_A_DEAD, age, 1); count_add(c, RB_A_NON_HOSPITAL_DEATHS, age, 1); }
-                else { h = H_SET_STATE(h, RB_RECOVERED) & ~H_LIST; count_add(c, RB_A_RECOVERED, age, 1); }
-            }
-            uint32_t idx = atomicAdd(&c->n_events, 1u);
-            if (idx < G.cap_events) {
-                G.ev_key[(size_t)r * G.cap_events + idx] = ((unsigned long long)sweep_pos(G, c, (uint32_t)a) << 2) | (unsigned)type;
-                G.ev_agent[(size_t)r * G.cap_events + idx] = a;
-            } else set_problem(c, RB_OTHER_FAILURE);
-        }
-    }
-    return n;
-}
-
-// The daily sweep.  Every warp streams its share of the packed words (coalesced 16-byte loads, 256 agents per
-// step), pushes the few agents that have anything to do today into a private shared-memory ring, and runs the state
-// machine only on full batches of 32 queued agents -- so the branchy part executes on dense warps, there is no
-// block-level barrier anywhere, and other warps keep the memory pipe busy meanwhile.  Contact work items are
-// allocated with a warp prefix sum and one atomic per batch and written cooperatively (coalesced).
+// The daily sweep = Context._iterate_people / _process_person / person_advance (main.pyx:1968-1992, 395-438).
+//
+// Every warp streams its share of the packed words (coalesced 16-byte loads, 256 agents per step) and pushes the
+// few agents that have anything to do today into a private shared-memory ring.  Work then flows through three
+// warp-private rings, each drained only in full batches of 32 so that every stage executes on dense warps and no
+// block-level barrier exists anywhere:
+//   ring A (active agents)   -> stage 1: R bookkeeping, "infected today" flag, day counters, transition detection
+//   ring E (infectious)      -> stage E: number of contacts (one Philox block + tabulated distribution), contact
+//                               work items allocated with a warp prefix sum + one atomic and written coalesced
+//   ring T (state changes)   -> stage T: symptom onset (gamma draw, durations, testing queue), end of illness,
+//                               ward / ICU exits (capacity events tagged with the agent's sweep position)
 #define SW_THREADS 256
 #define SW_WARPS (SW_THREADS / 32)
 #define SW_CHUNK 256
 #define SW_QCAP 512
-__device__ __forceinline__ void sweep_batch(const Eng &G, int r, RepCtr *c, const DevTable *tb, const uint32_t *qi, const uint32_t *qw,
-                                            uint32_t head, uint32_t m, uint2 *items, int lane) {
-    const size_t base = (size_t)r * G.Npad;
+#define SW_RCAP 64
+
+struct WarpRings {
+    uint32_t qi[SW_QCAP], qw[SW_QCAP];      // ring A: agent index, packed word
+    uint32_t ea[SW_RCAP], ed[SW_RCAP];      // ring E: agent index, contact descriptor
+    uint32_t ta[SW_RCAP], tw[SW_RCAP];      // ring T: agent index, packed word (day counters already advanced)
+};
+
+// warp-aggregated push of (x, y) for the lanes with `want` into a ring of SW_RCAP entries; returns the new tail
+__device__ __forceinline__ uint32_t ring_push(uint32_t *ra, uint32_t *rb, uint32_t tail, bool want, uint32_t x, uint32_t y, int lane) {
+    const uint32_t m = __ballot_sync(0xffffffffu, want);
+    if (want) { uint32_t p = (tail + __popc(m & ((1u << lane) - 1u))) & (SW_RCAP - 1); ra[p] = x; rb[p] = y; }
+    return tail + __popc(m);
+}
+
+// stage E: get_exposed_people / get_nr_contacts (main.pyx:936-955, 1308-1320) + work-item emission
+__device__ __forceinline__ void stage_expose(const Eng &G, RepCtr *c, const DevTable *tb, const WarpRings &W, uint32_t head, uint32_t m,
+                                             uint2 *items, int lane) {
     uint32_t cnt = 0, desc = 0, a = 0;
     if ((uint32_t)lane < m) {
-        a = qi[(head + lane) & (SW_QCAP - 1)];
-        uint32_t h = qw[(head + lane) & (SW_QCAP - 1)];
-        bool dirty = false;
-        cnt = advance_agent(G, r, c, tb, (int32_t)a, h, dirty, desc);
-        if (dirty) G.hot[base + a] = h;
+        a = W.ea[(head + lane) & (SW_RCAP - 1)];
+        desc = W.ed[(head + lane) & (SW_RCAP - 1)];
+        const int age = age_of(G, (int32_t)a);
+        const int cls = (desc >> 22) & 1u;
+        u32x4 x = philox(c->seed, a, (uint32_t)c->day, PU_NCONTACT, 0);
+        const double u = u01d(x.x, x.y);
+        const double *cdf = tb->ncdf[age][cls];
+        int lo = 0, hi = cls ? 5 : 100;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (u < __ldg(&cdf[mid])) hi = mid; else lo = mid + 1; }
+        cnt = (uint32_t)lo;
+        desc = (desc & ~(1u << 22)) | ((uint32_t)age << 7);
     }
     uint32_t incl = cnt;
 #pragma unroll
@@ -689,8 +587,7 @@ __device__ __forceinline__ void sweep_batch(const Eng &G, int r, RepCtr *c, cons
     if (gbase + wtot > G.cap_items) { if (lane == 0) set_problem(c, RB_OTHER_FAILURE); return; }
     for (uint32_t t0 = 0; t0 < wtot; t0 += 32) {
         const uint32_t t = t0 + lane;
-        // owner = largest lane whose exclusive prefix is <= t (lanes with zero contacts share a prefix with their successor)
-        int lo = 0;
+        int lo = 0;     // owner = largest lane whose exclusive prefix is <= t
 #pragma unroll
         for (int step = 16; step > 0; step >>= 1) {
             uint32_t e = __shfl_sync(0xffffffffu, excl, (lo + step) & 31);
@@ -701,9 +598,129 @@ __device__ __forceinline__ void sweep_batch(const Eng &G, int r, RepCtr *c, cons
     }
 }
 
+__device__ __forceinline__ void emit_event(const Eng &G, int r, RepCtr *c, int32_t a, int type) {
+    uint32_t idx = atomicAdd(&c->n_events, 1u);
+    if (idx < G.cap_events) {
+        G.ev_key[(size_t)r * G.cap_events + idx] = ((unsigned long long)sweep_pos(G, c, (uint32_t)a) << 2) | (unsigned)type;
+        G.ev_agent[(size_t)r * G.cap_events + idx] = a;
+    } else set_problem(c, RB_OTHER_FAILURE);
+}
+
+// stage T: the state changes of person_advance (main.pyx:405-438) for agents whose day counter reached zero
+__device__ __forceinline__ void stage_transition(const Eng &G, int r, RepCtr *c, const WarpRings &W, uint32_t head, uint32_t m, int lane) {
+    if ((uint32_t)lane >= m) return;
+    const size_t base = (size_t)r * G.Npad;
+    const int32_t a = (int32_t)W.ta[(head + lane) & (SW_RCAP - 1)];
+    uint32_t h = W.tw[(head + lane) & (SW_RCAP - 1)];
+    const int day = c->day;
+    const int age = age_of(G, a);
+    const uint32_t st = H_STATE(h), sev = H_SEV(h);
+    const rb_variant *v = &G.variants[H_VAR(h)];
+    if (st == RB_INCUBATION) {
+        // person_become_ill, main.pyx:284-291; durations :989-1039 fixed from the one onset-to-removed draw
+        float T = (sev == RB_FATAL)
+            ? gamma_f(c->seed, (uint32_t)a, (uint32_t)day, PU_ONSET, v->onset_death_kappa, v->onset_death_theta)
+            : gamma_f(c->seed, (uint32_t)a, (uint32_t)day, PU_ONSET, v->onset_recovery_kappa, v->onset_recovery_theta);
+        float f = T;
+        if (sev != RB_ASYMPTOMATIC && sev != RB_MILD) f = f * v->ratio_before_hospitalisation;
+        const uint32_t dl = (uint32_t)clamp255(round_to_int(f));
+        float w = 0.0f, u = 0.0f;
+        if (sev == RB_SEVERE) w = T * (1.0f - v->ratio_before_hospitalisation);
+        else if (sev == RB_CRITICAL || sev == RB_FATAL) {
+            w = T * v->ratio_in_ward;
+            u = ((1.0f - v->ratio_in_ward) - v->ratio_before_hospitalisation) * T;
+        }
+        const uint32_t wd = (uint32_t)clamp255(round_to_int(w)), ud = (uint32_t)clamp255(round_to_int(u));
+        if (wd | ud) atomicOr(&G.cold[base + a], (wd << 16) | (ud << 24));
+        h = H_SET_DL(H_SET_STATE(h, RB_ILLNESS), dl);
+        if (sev != RB_ASYMPTOMATIC && !(h & H_DET)) {
+            // seek_testing, main.pyx:595-615
+            bool q = false;
+            const int mode = c->testing_mode;
+            if (mode == RB_ALL_WITH_SYMPTOMS || mode == RB_ALL_WITH_SYMPTOMS_CT) q = true;
+            else if (mode == RB_ONLY_SEVERE_SYMPTOMS) {
+                if (sev >= RB_SEVERE) q = true;
+                else {
+                    u32x4 x = philox(c->seed, (uint32_t)a, (uint32_t)day, PU_SEEK, 0);
+                    q = chance(u01d(x.x, x.y), c->p_detected_anyway);
+                }
+            }
+            if (q && !(h & H_QUEUED)) {     // queue_for_testing guards (not DEAD / detected / queued), main.pyx:476
+                h |= H_QUEUED;
+                uint32_t idx = atomicAdd(&c->n_newq, 1u);
+                if (idx < G.cap_queue) {
+                    size_t qb = ((size_t)r * 2 + (c->qsel ^ 1u)) * G.cap_queue;
+                    G.q_key[qb + idx] = QKEY_SWEEP | sweep_pos(G, c, (uint32_t)a);
+                    G.q_agent[qb + idx] = a;
+                } else set_problem(c, RB_OTHER_FAILURE);
+            }
+        }
+    } else if (st == RB_ILLNESS) {
+        if (sev == RB_FATAL) {                       // person_die, main.pyx:370-374, 1618-1623
+            h = H_SET_STATE(h, RB_DEAD) & ~H_LIST;
+            count_add(c, RB_A_INFECTED, age, -1); count_add(c, RB_A_DEAD, age, 1); count_add(c, RB_A_NON_HOSPITAL_DEATHS, age, 1);
+        } else if (sev >= RB_SEVERE) {               // person_hospitalize, main.pyx:321-338: the bed claim is an event
+            if (!(h & H_DET)) { h |= H_DET; count_add(c, RB_A_DETECTED, age, 1); count_add(c, RB_A_ALL_DETECTED, age, 1); }
+            emit_event(G, r, c, a, EV_HOSP_CLAIM);
+        } else {                                     // person_recover, main.pyx:315-318
+            h = H_SET_STATE(h, RB_RECOVERED) & ~H_LIST;
+            count_add(c, RB_A_INFECTED, age, -1); count_add(c, RB_A_RECOVERED, age, 1);
+        }
+    } else {   // HOSPITALIZED / IN_ICU
+        int type;
+        if (st == RB_HOSPITALIZED && (sev == RB_CRITICAL || sev == RB_FATAL)) type = EV_TO_ICU;   // main.pyx:430-431
+        else {
+            // person_release_from_hospital, main.pyx:354-367: the outcome does not depend on capacity
+            type = st == RB_IN_ICU ? EV_ICU_RELEASE : EV_WARD_RELEASE;
+            count_add(c, st == RB_IN_ICU ? RB_A_IN_ICU : RB_A_IN_WARD, age, -1);
+            count_add(c, RB_A_INFECTED, age, -1);
+            if (sev == RB_FATAL) { h = H_SET_STATE(h, RB_DEAD) & ~H_LIST; count_add(c, RB_A_DEAD, age, 1); count_add(c, RB_A_NON_HOSPITAL_DEATHS, age, 1); }
+            else { h = H_SET_STATE(h, RB_RECOVERED) & ~H_LIST; count_add(c, RB_A_RECOVERED, age, 1); }
+        }
+        emit_event(G, r, c, a, type);
+    }
+    G.hot[base + a] = h;
+}
+
+// stage 1 over one batch of ring A; pushes to rings E and T
+__device__ __forceinline__ void stage_active(const Eng &G, int r, RepCtr *c, WarpRings &W, uint32_t head, uint32_t m,
+                                             uint32_t &e_tail, uint32_t &t_tail, int lane) {
+    const size_t base = (size_t)r * G.Npad;
+    bool want_e = false, want_t = false;
+    uint32_t a = 0, h = 0, desc = 0;
+    if ((uint32_t)lane < m) {
+        a = W.qi[(head + lane) & (SW_QCAP - 1)];
+        h = W.qw[(head + lane) & (SW_QCAP - 1)];
+        const uint32_t st = H_STATE(h);
+        if (st >= RB_RECOVERED) {          // R bookkeeping, main.pyx:1969-1972 (only agents not yet included reach here)
+            atomicAdd(&c->total_infectors, 1);
+            atomicAdd(&c->total_infections, (int)(G.cold[base + a] & 0xffffu));
+            G.hot[base + a] = h | H_INCL;
+        } else if (h & H_FRESH) {          // infected today before the sweep: wait until tomorrow, main.pyx:402-403
+            G.hot[base + a] = h & ~H_FRESH;
+        } else {
+            const uint32_t sev = H_SEV(h), var = H_VAR(h);
+            uint32_t dl = H_DL(h);
+            if (st == RB_INCUBATION || st == RB_ILLNESS) {
+                const int dayidx = st == RB_INCUBATION ? -(int)dl : (int)H_DOI(h);
+                if (!(h & H_DET) && dayidx >= -10 && dayidx <= 10 && G.variants[var].iot[dayidx + 10] != 0.0f) {
+                    want_e = true;
+                    const uint32_t cls = (st == RB_ILLNESS && sev != RB_ASYMPTOMATIC) ? 1u : 0u;   // factor 0.5, limit 5
+                    desc = ((uint32_t)(dayidx + 10) << 14) | ((sev == RB_ASYMPTOMATIC ? 1u : 0u) << 19) | (var << 20) | (cls << 22);
+                }
+                if (st == RB_ILLNESS) { uint32_t doi = H_DOI(h); if (doi < 31) doi++; h = H_SET_DOI(h, doi); }
+            }
+            if (dl > 0) dl--;
+            h = H_SET_DL(h, dl);
+            if (dl == 0) want_t = true; else G.hot[base + a] = h;
+        }
+    }
+    e_tail = ring_push(W.ea, W.ed, e_tail, want_e, a, desc, lane);
+    t_tail = ring_push(W.ta, W.tw, t_tail, want_t, a, h, lane);
+}
+
 __global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
-    __shared__ uint32_t s_qi[SW_WARPS][SW_QCAP];   // queued agent index
-    __shared__ uint32_t s_qw[SW_WARPS][SW_QCAP];   // its packed word
+    __shared__ WarpRings s_rings[SW_WARPS];
     const int r = blockIdx.y;
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
@@ -711,10 +728,10 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
     const uint4 *hot4 = reinterpret_cast<const uint4 *>(G.hot + base);
     uint2 *items = G.items + (size_t)r * G.cap_items;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *qi = s_qi[warp], *qw = s_qw[warp];
+    WarpRings &W = s_rings[warp];
     const int n_chunks = (G.Npad + SW_CHUNK - 1) / SW_CHUNK;
     const int n4 = G.Npad >> 2;
-    uint32_t head = 0, tail = 0;
+    uint32_t head = 0, tail = 0, e_head = 0, e_tail = 0, t_head = 0, t_tail = 0;
     for (int chunk = blockIdx.x * SW_WARPS + warp; chunk < n_chunks; chunk += gridDim.x * SW_WARPS) {
         const int a0 = chunk * SW_CHUNK;
         const int i0 = (a0 >> 2) + lane, i1 = i0 + 32;
@@ -737,16 +754,25 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
 #pragma unroll
         for (int j = 0; j < 8; j++)
             if (act & (1u << j)) {
-                qi[p & (SW_QCAP - 1)] = (uint32_t)(a0 + (j < 4 ? lane * 4 + j : 128 + lane * 4 + (j - 4)));
-                qw[p & (SW_QCAP - 1)] = hw[j];
+                W.qi[p & (SW_QCAP - 1)] = (uint32_t)(a0 + (j < 4 ? lane * 4 + j : 128 + lane * 4 + (j - 4)));
+                W.qw[p & (SW_QCAP - 1)] = hw[j];
                 p++;
             }
         tail += tot;
         __syncwarp();
-        while (tail - head >= 32) { sweep_batch(G, r, c, tb, qi, qw, head, 32, items, lane); head += 32; }
-        __syncwarp();
+        while (tail - head >= 32) {
+            stage_active(G, r, c, W, head, 32, e_tail, t_tail, lane); head += 32;
+            __syncwarp();
+            if (e_tail - e_head >= 32) { stage_expose(G, c, tb, W, e_head, 32, items, lane); e_head += 32; }
+            if (t_tail - t_head >= 32) { stage_transition(G, r, c, W, t_head, 32, lane); t_head += 32; }
+            __syncwarp();
+        }
     }
-    if (tail != head) sweep_batch(G, r, c, tb, qi, qw, head, tail - head, items, lane);
+    // drain: whatever is left in ring A, then rings E and T (at most two partial batches each)
+    if (tail != head) { stage_active(G, r, c, W, head, tail - head, e_tail, t_tail, lane); }
+    __syncwarp();
+    while (e_tail != e_head) { uint32_t m = min(32u, e_tail - e_head); stage_expose(G, c, tb, W, e_head, m, items, lane); e_head += m; }
+    while (t_tail != t_head) { uint32_t m = min(32u, t_tail - t_head); stage_transition(G, r, c, W, t_head, m, lane); t_head += m; }
 }
 
 // ---------------------------------------------------------------- k_expose
