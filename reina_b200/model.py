@@ -323,7 +323,7 @@ class Context:
         # pending one-day effects collected by apply_intervention
         self._pending = dict(beds=0, icu=0, imports=[])
         self._epoch = 0
-        self._epoch_mobility = {0: float(1 - self.contact_matrix.mobility_factor)}
+        self._epoch_mobility = {0: 1 - float(self.contact_matrix.mobility_factor)}
         self._tables = {0: self.contact_matrix.generate()}
         self._engine.set_contact_table(0, self._tables[0])
         self._plan = []         # DayParams of every day planned so far (the schedule does not depend on the seed)
@@ -511,7 +511,7 @@ class Context:
             self._epoch += 1
             self._tables[self._epoch] = cm.generate()
             self._engine.set_contact_table(self._epoch, self._tables[self._epoch])
-            self._epoch_mobility[self._epoch] = float(1 - cm.mobility_factor)
+            self._epoch_mobility[self._epoch] = 1 - float(cm.mobility_factor)
             cm.mobility_factor_changed = False
         dp.table_epoch = self._epoch
         # infect_people_daily, main.pyx:1671-1685 (C float accumulator, Python-float arithmetic)

@@ -1,0 +1,163 @@
+"""Host-side logic: contact tables, intervention schedule, the Context surface (run on the CPU oracle library),
+and that both shared libraries export every symbol of include/reina_b200.h."""
+import re
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from reina_b200 import _abi, inputs, model
+
+
+def test_libraries_export_every_declared_symbol():
+    hdr = open(os.path.join(helpers.ROOT, 'include', 'reina_b200.h')).read()
+    declared = sorted(set(re.findall(r'\brb_([a-z_]+)\s*\(', hdr)))
+    assert set(declared) == set(_abi.SYMBOLS), set(declared) ^ set(_abi.SYMBOLS)
+    cuda = _abi.Library(_abi.CUDA_LIB_PATH, 'rb_')          # loads without a GPU; no compute call is made
+    orac = helpers.oracle_library()
+    for name in declared:
+        assert hasattr(cuda.dll, 'rb_' + name) and hasattr(orac.dll, 'ro_' + name), name
+
+
+def test_no_cpu_fallback(tmp_path):
+    """The product must fail loudly when its CUDA library is missing, and creating a Context without a GPU fails."""
+    with pytest.raises(_abi.EngineError):
+        _abi.Library(str(tmp_path / 'libreina_b200.so'), 'rb_')
+    import ctypes
+    ndev = ctypes.c_int(0)
+    try:
+        rc = ctypes.CDLL('libcudart.so').cudaGetDeviceCount(ctypes.byref(ndev))
+    except OSError:
+        rc = 1
+    if rc != 0 or ndev.value == 0:
+        with pytest.raises(_abi.EngineError, match='no CUDA device|CUDA'):
+            helpers.make_context(_abi.cuda_library(), age_count_override=helpers.small_population(2000))
+
+
+def _pandas_tables(cm):
+    """ContactMatrix.generate_contact_probabilities restated with the pandas operations of main.pyx:1195-1235."""
+    import pandas as pd
+    recs = []
+    for (place, band), col in zip(cm.keys, range(len(cm.keys))):
+        for age in range(cm.n_ages):
+            recs.append((place, age, band, cm.base[age, col]))
+    df = pd.DataFrame(recs, columns=['place_type', 'participant_age', 'contact_age', 'contacts'])
+    for place, min_age, max_age, factor in cm.mobility_factors:
+        if factor == 1.0:
+            continue
+        flt = (df.participant_age >= min_age) & (df.participant_age <= max_age)
+        if place != model.PLACE_ALL:
+            flt &= df.place_type == model.CONTACT_PLACE_TO_STR[place]
+        df.loc[flt, 'contacts'] *= float(factor)
+    total = df.groupby('participant_age')['contacts'].sum()
+    df = df.set_index(['place_type', 'participant_age', 'contact_age']).sort_index()
+    df = df.unstack('participant_age')
+    df.columns = df.columns.droplevel(0)
+    cum = df.divide(total, axis=1).cumsum()
+    return total.values, cum.values.T, list(cum.index)
+
+
+def test_contact_tables_match_pandas_restatement():
+    cm = model.ContactMatrix(inputs.contacts_long(), 101)
+    cm.set_mobility_factor(0.2, place=5, min_age=0, max_age=70)
+    cm.set_mobility_factor(0.95)
+    cm.set_mobility_factor(0.0, place=2, min_age=19, max_age=None)
+    cm.set_mask_probability(0.8, min_age=65)
+    t = cm.generate()
+    total, cum, index = _pandas_tables(cm)
+    nk = len(cm.keys)
+    assert [(p, b) for p, b in index] == cm.keys                     # row order: place name, then band
+    np.testing.assert_allclose(t['nr_contacts'], total, rtol=1e-12)
+    np.testing.assert_allclose(t['cum_p'][:, :nk], cum, rtol=0, atol=1e-12)
+    assert (np.diff(t['cum_p'][:, :nk], axis=1) >= 0).all()
+    assert t['mask_p'][70, 0] == np.float32(0.8) and t['mask_p'][30, 0] == 0
+    assert cm.mobility_factor == np.float32(0.0)                      # last factor set, any key (main.pyx:1251)
+    # tabulated number-of-contacts distribution: monotone, and equal to the sampled lognormal rule
+    cdf = t['ncontact_cdf']
+    assert (np.diff(cdf[:, 0, :], axis=1) >= 0).all() and (cdf <= 1).all()
+    rng = np.random.default_rng(5)
+    c = total[30]
+    f = np.maximum(rng.lognormal(0, 0.5, 400000) * c, 1.0).astype(np.int64) - 1
+    emp = (np.minimum(f, 100)[:, None] <= np.arange(6)[None, :]).mean(0)
+    np.testing.assert_allclose(emp, cdf[30, 0, :6], atol=4e-3)
+
+
+def test_intervention_tuples_and_schedule(oracle_lib):
+    ivs = inputs.active_interventions()
+    assert len(ivs) == 40 and ivs[6].get_param_values() == dict(reduction=80, min_age=0, max_age=70, place='other')
+    assert inputs.iv_tuple_to_obj(['wear-masks', '2020-07-01', 80, 65, None, None]).get_param_values() == \
+        dict(share_of_contacts=80, min_age=65)
+    assert len(inputs.scenario_interventions('mitigation')) == 58
+    halved = inputs.scenario_interventions('looser-restrictions-to-start-with')
+    assert halved[6][2] == 40 and halved[8][2] == 2
+    ctx = helpers.make_context(oracle_lib, age_count_override=helpers.small_population(5000), max_days=300)
+    ctx.run(260)
+    plan = ctx._plan
+    assert [plan[d].testing_mode for d in (0, 2, 26, 118)] == [0, 2, 3, 1]          # NO_TESTING, ALL, ONLY_SEVERE, CT
+    assert abs(plan[41].p_detected_anyway - 0.5) < 1e-6 and abs(plan[118].p_successful_tracing - 0.3) < 1e-6
+    assert plan[4].n_imports == 1 and plan[4].import_amount[0] == 20                 # 2020-02-22
+    # 50 / week from 2020-07-01 through a C-float accumulator (main.pyx:1671-1685): 7 x 7.142857 truncates to 49
+    assert sum(p.trickle[0] for p in plan[134:141]) in (49, 50) and 498 <= sum(p.trickle[0] for p in plan[134:204]) <= 500
+    assert sum(p.trickle[0] for p in plan[:134]) == 0
+    epochs = [p.table_epoch for p in plan]
+    assert epochs[0] == 0 and epochs[23] == 1 and max(epochs) == 11 and sorted(set(epochs)) == list(range(12))
+    s = ctx.generate_state()
+    assert abs(s['mobility_limitation'] - (1 - np.float32(1.0))) < 1e-6
+    assert ctx.get_date_for_today() == '2020-11-04'
+
+
+def test_context_surface(oracle_lib):
+    ctx = helpers.make_context(oracle_lib, age_count_override=helpers.small_population(8000), seed=3)
+    s0 = ctx.generate_state()
+    assert set(s0) >= {'available_icu_units', 'available_hospital_beds', 'total_icu_units', 'r', 'exposed_per_day',
+                       'ct_cases_per_day', 'mobility_limitation', 'infected_by_variant', 'daily_contacts', *_abi.ATTRS}
+    assert s0['susceptible'].dtype == np.int32 and s0['susceptible'].sum() == 8000 and s0['infected'].sum() == 0
+    assert list(s0['infected_by_variant']) == ['wild-type', 'b1.1.7']
+    assert list(s0['daily_contacts']) == ['home', 'work', 'school', 'transport', 'leisure', 'other']
+    for _ in range(30):
+        ctx.iterate()
+    s = ctx.generate_state()
+    tot = sum(s[k].sum() for k in ('susceptible', 'infected', 'recovered', 'dead'))
+    assert tot == 8000 and s['all_infected'].sum() > 0
+    assert (ctx.get_population_stats('all_infected') >= 0).all() and len(ctx.get_population_stats('dead')) == 101
+    with pytest.raises(Exception):
+        ctx.get_population_stats('nonsense')
+    with pytest.raises(Exception):
+        ctx.apply_intervention(inputs.Intervention('no-such-intervention', '2020-01-01'))
+    assert model.PROBLEM_TO_STR[7] == 'Wrong state' and model.SEVERITY_TO_STR[4] == 'FATAL'
+    assert model.DISEASE_PARAMS[0] == 'p_susceptibility' and len(model.DISEASE_PARAMS) == 18
+    # reset(): a fresh run with another seed, same plan
+    ctx.reset(77)
+    assert ctx.day == 0 and ctx.generate_state()['infected'].sum() == 0
+
+
+def test_ensemble_replicas_and_reset(oracle_lib):
+    counts = helpers.small_population(6000)
+    a = helpers.make_context(oracle_lib, age_count_override=counts, seed=10, n_replicas=2)
+    a.run(60)
+    rows = a.series(0, 60)
+    b = helpers.make_context(oracle_lib, age_count_override=counts, seed=11)
+    b.run(60)
+    assert np.array_equal(rows[1], b.series(0, 60)[0])
+    a.reset(11)
+    a.run(60)
+    assert np.array_equal(a.series(0, 60)[0], rows[1])
+
+
+def test_simulate_individuals_shapes(oracle_lib):
+    from reina_b200 import simulation
+    v = inputs.default_variables(simulation_days=25)
+    ctx = helpers.make_context(oracle_lib, variables=v, age_count_override=helpers.small_population(4000), max_days=30)
+    seen = []
+    df, adf = simulation.simulate_individuals(v, context=ctx, step_callback=lambda d: seen.append(len(d.dropna())) or True,
+                                              callback_day_interval=10)
+    assert seen == [10, 20, 25]
+    assert list(df.columns) == simulation.POP_ATTRS + simulation.STATE_ATTRS + simulation.EXPOSURES_ATTRS + ['us_per_infected']
+    assert df.shape == (25, 26) and adf.shape == (25, 12 * 9)
+    assert adf.columns.names == ['attr', 'age_group'] and ('dead', '80+') in adf.columns
+    assert df['susceptible'].iloc[0] == 4000
+    with pytest.raises(simulation.ExecutionInterrupted):
+        simulation.simulate_individuals(v, context=helpers.make_context(
+            oracle_lib, variables=v, age_count_override=helpers.small_population(4000), max_days=30),
+            step_callback=lambda d: False)

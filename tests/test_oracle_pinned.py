@@ -1,0 +1,120 @@
+"""Pin the CPU oracle against outputs of the UNMODIFIED reference engine (tests/golden/, made by
+tests/golden/make_golden*.py from oracle/_ref in the build container).
+
+The reference has no golden vectors of its own for this path, and its single sequential
+PCG64 stream cannot be reproduced by any parallel schedule, so the pin is statistical, as north_star prescribes:
+ensemble means of every daily series within 3 standard errors, and the samplers' distributions equal.
+The CUDA engine is then held BIT-EXACT to this oracle (tests/test_gpu_parity.py).
+"""
+import os
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+import pytest
+from scipy import stats
+
+import helpers
+
+GOLD = os.path.join(helpers.ROOT, 'tests', 'golden')
+
+
+def _oracle_run(job):
+    area, seed, days = job
+    ctx = helpers.make_context(helpers.oracle_library(), area=area, seed=seed, max_days=days + 1)
+    ctx.run(days)
+    return helpers.series_matrix(ctx)[0]
+
+
+def zscores(mine, gold):
+    """z of the difference of ensemble means per (day, series); cells without variance on either side must agree."""
+    m2, s2, n2 = mine.mean(0), mine.std(0, ddof=1), mine.shape[0]
+    se = np.sqrt(gold['std'] ** 2 / int(gold['n']) + s2 ** 2 / n2)
+    diff = m2 - gold['mean']
+    with np.errstate(divide='ignore', invalid='ignore'):
+        z = np.where(se > 0, diff / se, 0.0)
+    exact = (se == 0) & (np.abs(diff) > 1e-9)
+    return z, exact
+
+
+def test_ensemble_means_within_3_standard_errors():
+    """Varsinais-Suomi (BASELINE configs[0]), 180 days, 24 oracle seeds vs 256 reference seeds."""
+    gold = np.load(os.path.join(GOLD, 'ref_ensemble_varsinais_suomi_default_n256.npz'))
+    with ProcessPoolExecutor(min(8, os.cpu_count() or 1)) as ex:
+        runs = list(ex.map(_oracle_run, [('Varsinais-Suomi', 7000 + s, 180) for s in range(24)]))
+    mine = np.stack(runs)
+    assert list(gold['names']) == helpers.series_names()
+    z, exact = zscores(mine, gold)
+    names = list(gold['names'])
+    assert not exact.any(), 'deterministic series differ: %s' % sorted({names[j] for j in np.argwhere(exact)[:, 1]})
+    frac = (np.abs(z) > 3).mean()
+    worst = np.unravel_index(np.abs(z).argmax(), z.shape)
+    # 180 x 28 cells: at 3 SE about 0.3 % exceed by chance; series are strongly autocorrelated, so allow 1.5 %
+    assert frac < 0.015, 'fraction of cells beyond 3 SE: %.4f' % frac
+    assert np.abs(z).max() < 5.0, 'worst cell: day %d %s z=%.2f' % (worst[0], names[worst[1]], z[worst])
+    # the headline totals on the last day, within 3 SE
+    for s in ('all_infected', 'dead', 'all_detected', 'recovered', 'cum_icu'):
+        assert abs(z[-1, names.index(s)]) < 3.0, (s, z[-1, names.index(s)])
+
+
+def _chi2_same(a, b, min_expected=20):
+    """Two count histograms drawn from the same distribution? (pooled bins, chi-square contingency test)"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    keep = (a + b) >= min_expected
+    a2 = np.append(a[keep], a[~keep].sum())
+    b2 = np.append(b[keep], b[~keep].sum())
+    ok = (a2 + b2) > 0
+    return stats.chi2_contingency(np.stack([a2[ok], b2[ok]]))[1]
+
+
+@pytest.fixture(scope='module')
+def sample_ctx(oracle_lib):
+    return helpers.make_context(oracle_lib, area='Varsinais-Suomi', seed=99)
+
+
+def test_contacts_and_severity_samplers_match_reference(sample_ctx):
+    """Context.sample('contacts_per_day' | 'symptom_severity', age) vs 400k draws of the reference per age."""
+    gold = np.load(os.path.join(GOLD, 'ref_samples.npz'))
+    for age in gold['ages']:
+        mine_c = np.zeros(101)
+        mine_s = np.zeros(5)
+        for rep in range(8):
+            # the oracle's sample() keys its draws on (i, age, kind); vary the seed through reset-free contexts
+            sample_ctx._engine.reset(1234 + 17 * rep)
+            mine_c += np.bincount(sample_ctx.sample('contacts_per_day', int(age)), minlength=101)[:101]
+            mine_s += np.bincount(sample_ctx.sample('symptom_severity', int(age)), minlength=5)[:5]
+        p_c = _chi2_same(mine_c, gold['contacts_%d' % age])
+        p_s = _chi2_same(mine_s, gold['severity_%d' % age])
+        assert p_c > 1e-3, ('contacts_per_day', int(age), p_c)
+        assert p_s > 1e-3, ('symptom_severity', int(age), p_s)
+
+
+def _numpy_gamma_days(mu, cv, scale, n, seed):
+    """Restatement of simrandom.pyx:46-55 + main.pyx:773-774 with numpy's own float32 gamma."""
+    f = np.float32
+    sigma = f(cv) * f(mu)
+    theta = f(f(sigma * sigma) / f(mu))
+    kappa = f(f(mu) / theta)
+    g = np.random.Generator(np.random.PCG64(seed)).standard_gamma(float(kappa), size=n, dtype=np.float32)
+    return ((g * theta) * f(scale) + f(0.5)).astype(np.int32)
+
+
+@pytest.mark.parametrize('what,severity,mu,cv,scale', [
+    ('incubation_period', 'MILD', 5.1, 0.86, 1.0),             # main.pyx:977-986
+    ('onset_to_removed_period', 'MILD', 21.0, 0.45, 1.0),      # main.pyx:989-1001
+    ('onset_to_removed_period', 'FATAL', 18.8, 0.45, 1.0),
+    ('illness_period', 'MILD', 21.0, 0.45, 1.0),               # main.pyx:1004-1014
+    ('illness_period', 'SEVERE', 21.0, 0.45, 0.30),
+    ('hospitalization_period', 'SEVERE', 21.0, 0.45, 0.70),    # main.pyx:1016-1027
+    ('hospitalization_period', 'CRITICAL', 21.0, 0.45, 0.15),
+    ('icu_period', 'CRITICAL', 21.0, 0.45, 0.55),              # main.pyx:1029-1039
+])
+def test_duration_samplers_ks(sample_ctx, what, severity, mu, cv, scale):
+    """KS test of the sampled disease durations against numpy's legacy float32 gamma (what the reference links)."""
+    mine = np.concatenate([
+        (sample_ctx._engine.reset(500 + k), sample_ctx.sample(what, 40, severity))[1] for k in range(5)])
+    ref = _numpy_gamma_days(mu, cv, scale, 200000, seed=1)
+    # integer-valued samples: jitter uniformly inside the unit bin so that ties do not bias the KS statistic
+    rng = np.random.default_rng(0)
+    d, p = stats.ks_2samp(mine + rng.random(mine.size), ref + rng.random(ref.size))
+    assert p > 1e-3, (what, severity, d, p)
+    assert abs(mine.mean() - ref.mean()) < 0.05 * max(1.0, ref.mean())
