@@ -120,13 +120,11 @@ def cpu_baseline(days, seeds, processes):
     if ref_harness.available():
         t0 = time.perf_counter()
         _, t_iter, wall = ref_harness.run_ensemble(seeds, days=days, processes=processes, area=AREA)
-        if processes == 1:
-            value = N_AGENTS * days * len(seeds) / float(t_iter.sum())
-        else:
-            value = N_AGENTS * days * len(seeds) / wall
+        # rate of each core = agent-days of its run / time spent inside iterate() (setup excluded); cores add up
+        value = float((N_AGENTS * days / t_iter).sum()) if processes > 1 else N_AGENTS * days * len(seeds) / float(t_iter.sum())
         return dict(value=value, unit='agent-days/s', cores=processes, kind='reference',
                     sample='%d seed(s) x HUS %d days, unmodified cythonsim engine (oracle/_ref), %s'
-                           % (len(seeds), days, 'sum of iterate() time' if processes == 1 else 'wall time of the process pool'),
+                           % (len(seeds), days, 'sum of iterate() time' if processes == 1 else 'sum over cores of agent-days / iterate() time'),
                     seconds=time.perf_counter() - t0)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import helpers

@@ -66,7 +66,7 @@ typedef struct rb_variant {
     float incubation_kappa, incubation_theta;      /* main.pyx:977-986  (cv 0.86) */
     float onset_death_kappa, onset_death_theta;    /* main.pyx:989-1001 (cv 0.45, FATAL) */
     float onset_recovery_kappa, onset_recovery_theta;
-    float reserved[2];
+    float reserved[2];                             /* [0] = max over ages of tab[RB_T_SUSCEPTIBILITY] (transmission upper bound) */
     float iot[RB_IOT_LEN + 3];                     /* index = day + 10 */
     float tab[RB_N_TABLES][RB_MAX_AGES];
 } rb_variant;

@@ -40,7 +40,7 @@
 #define MAX_CONTACTS 128   /* main.pyx:129 */
 
 enum { PU_START = 1, PU_NCONTACT, PU_CONTACT, PU_SEVERITY, PU_INCUB, PU_ONSET, PU_SEEK, PU_NOBED,
-       PU_TRACE, PU_IMPORT, PU_PERM, PU_SAMPLE };
+       PU_TRACE, PU_IMPORT, PU_PERM, PU_SAMPLE, PU_CONTACT2 };
 #define KEY1 0x5EEDB200u
 
 typedef struct {
@@ -473,24 +473,33 @@ static int person_expose_others(rb_engine *e, Replica *r, int32_t ai) {
     const rb_variant *v = &e->variants[p->variant];
     if (p->severity == RB_ASYMPTOMATIC) si = si * v->p_asymptomatic_infection;
     int nrows = tb->n_rows[p->age];
+    /* Thinning (distribution-preserving restatement of did_infect, main.pyx:908-934): no target can be infected with
+     * probability above p_upper = si * max susceptibility * multiplier, so a contact first passes a coarse 8-bit
+     * filter with probability q = k/256 >= p_upper, and only then is its person drawn and the transmission decided
+     * with probability p/q.  Four contacts share one Philox block: 24 bits pick the row, 8 bits feed the filter. */
+    float p_upper = (si * v->reserved[0]) * v->infectiousness_multiplier;
+    int kq = (int)(p_upper * 256.0f) + 1;
+    if (kq > 256) kq = 256;
     for (int slot = 0; slot < n; slot++) {
         uint32_t x[4];
-        philox(r->seed, KEY1, (uint32_t)ai, (uint32_t)e->day, PU_CONTACT | ((uint32_t)slot << 8), 0, x);
-        /* one Philox block per contact: word 0 -> row, 1 -> person within the band, 2 -> transmission, 3 -> mask */
-        double u = (double)x[0] * (1.0 / 4294967296.0);
+        philox(r->seed, KEY1, (uint32_t)ai, (uint32_t)e->day, PU_CONTACT | ((uint32_t)(slot >> 2) << 8), 0, x);
+        uint32_t word = x[slot & 3];
+        double u = (double)(word >> 8) * (1.0 / 16777216.0);
         int row = nrows - 1;   /* the reference fails with CONTACT_PROBABILITY_FAILURE here (p ~ 1e-15) */
         for (int i = 0; i < nrows; i++) if (u < tb->cum_p[p->age][i]) { row = i; break; }
-        int32_t ti = tb->start[p->age][row] + (int32_t)(x[1] % (uint32_t)tb->size[p->age][row]);
         r->daily_contacts[tb->place[p->age][row]] += 1;
+        if ((int)(word & 255u) >= kq) continue;
+        philox(r->seed, KEY1, (uint32_t)ai, (uint32_t)e->day, PU_CONTACT2 | ((uint32_t)slot << 8), 0, x);
+        int32_t ti = tb->start[p->age][row] + (int32_t)(x[0] % (uint32_t)tb->size[p->age][row]);
         Agent *t = &r->agents[ti];
         if (t->state != RB_SUSCEPTIBLE) continue;       /* person_expose, main.pyx:238-244 */
         float pr = (si * v->tab[RB_T_SUSCEPTIBILITY][t->age]) * v->infectiousness_multiplier;
-        if (!chance((double)x[2] * (1.0 / 4294967296.0), pr)) continue;
+        if (!(((double)x[1] * (1.0 / 4294967296.0)) * (double)kq < (double)pr * 256.0)) continue;
         float mp = tb->mask_p[p->age][row];
         if (mp != 0.0f) {
             float a = mp * v->p_mask_protects_others, b = mp * v->p_mask_protects_wearer;
             float pm = (a + b) - a * b;
-            if (chance((double)x[3] * (1.0 / 4294967296.0), pm)) continue;
+            if (chance((double)x[2] * (1.0 / 4294967296.0), pm)) continue;
         }
         person_infect(e, r, ti, ai, -1, slot);
         if (p->has_list && p->n_infected >= MAX_INFECTEES) { r->problem = RB_TOO_MANY_INFECTEES; break; }

@@ -72,6 +72,7 @@ struct DevTable {
     uint8_t lo_age[RB_MAX_AGES][RB_MAX_ROWS], hi_age[RB_MAX_AGES][RB_MAX_ROWS];
     uint8_t susc_uniform[RB_MAX_AGES][RB_MAX_ROWS];   // susceptibility identical for every age of the row's band
     uint8_t guide[RB_MAX_AGES][256];                  // first row whose cum_p exceeds b/256: start of the row search
+    uint8_t nguide[RB_MAX_AGES][2][64];               // first k with ncdf[k] > b/64: start of the contact-count search
 };
 
 struct Attempt { uint32_t cand, parent; unsigned long long key; };
@@ -111,15 +112,17 @@ struct Eng {
     DevTable *const *tables;
     const rb_variant *variants;
     const int32_t *age_start;                      // [n_ages+1]
+    const uint8_t *age_blk;                        // age of agent (b << 10): coarse index into age_start
     const int32_t *group_of_age;
     const int32_t *import_lo, *import_hi; const float *import_cum;
 };
 
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ int age_of(const Eng &G, int32_t a) {
-    int lo = 0, hi = G.n_ages;
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(&G.age_start[mid]) <= a) lo = mid; else hi = mid; }
-    return lo;
+    // agents are age-sorted: start from the age of the 1024-agent block and walk up (0-1 steps at HUS sizes)
+    int age = __ldg(&G.age_blk[a >> 10]);
+    while (a >= __ldg(&G.age_start[age + 1])) age++;
+    return age;
 }
 __device__ __forceinline__ int age_in_band(const Eng &G, int32_t a, int lo, int hi) {   // age of agent a, known to lie in [lo, hi]
     hi += 1;
@@ -561,7 +564,7 @@ __device__ __forceinline__ uint32_t ring_push(uint32_t *ra, uint32_t *rb, uint32
 // stage E: get_exposed_people / get_nr_contacts (main.pyx:936-955, 1308-1320) + work-item emission
 __device__ __forceinline__ void stage_expose(const Eng &G, RepCtr *c, const DevTable *tb, const WarpRings &W, uint32_t head, uint32_t m,
                                              uint2 *items, int lane) {
-    uint32_t cnt = 0, desc = 0, a = 0;
+    uint32_t cnt = 0, ncont = 0, desc = 0, a = 0;
     if ((uint32_t)lane < m) {
         a = W.ea[(head + lane) & (SW_RCAP - 1)];
         desc = W.ed[(head + lane) & (SW_RCAP - 1)];
@@ -569,10 +572,13 @@ __device__ __forceinline__ void stage_expose(const Eng &G, RepCtr *c, const DevT
         const int cls = (desc >> 22) & 1u;
         u32x4 x = philox(c->seed, a, (uint32_t)c->day, PU_NCONTACT, 0);
         const double u = u01d(x.x, x.y);
+        // n = first k with u < cdf[k] (k = limit if none); entries below nguide[u's top 6 bits] cannot match
         const double *cdf = tb->ncdf[age][cls];
-        int lo = 0, hi = cls ? 5 : 100;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (u < __ldg(&cdf[mid])) hi = mid; else lo = mid + 1; }
-        cnt = (uint32_t)lo;
+        const int limit = cls ? 5 : 100;
+        int k = tb->nguide[age][cls][x.x >> 26];
+        while (k < limit && !(u < __ldg(&cdf[k]))) k++;
+        ncont = (uint32_t)k;
+        cnt = (ncont + 3u) >> 2;          // work items are groups of four contact slots (they share one Philox block)
         desc = (desc & ~(1u << 22)) | ((uint32_t)age << 7);
     }
     uint32_t incl = cnt;
@@ -582,7 +588,10 @@ __device__ __forceinline__ void stage_expose(const Eng &G, RepCtr *c, const DevT
     if (wtot == 0) return;
     const uint32_t excl = incl - cnt;
     uint32_t gbase = 0;
-    if (lane == 31) { gbase = atomicAdd(&c->n_items, wtot); atomicAdd(&c->exposed_per_day, (int)wtot); }
+    uint32_t ctot = ncont;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ctot += __shfl_xor_sync(0xffffffffu, ctot, o);
+    if (lane == 31) { gbase = atomicAdd(&c->n_items, wtot); atomicAdd(&c->exposed_per_day, (int)ctot); }
     gbase = __shfl_sync(0xffffffffu, gbase, 31);
     if (gbase + wtot > G.cap_items) { if (lane == 0) set_problem(c, RB_OTHER_FAILURE); return; }
     for (uint32_t t0 = 0; t0 < wtot; t0 += 32) {
@@ -594,7 +603,11 @@ __device__ __forceinline__ void stage_expose(const Eng &G, RepCtr *c, const DevT
             if (lo + step < 32 && e <= t) lo += step;
         }
         const uint32_t oa = __shfl_sync(0xffffffffu, a, lo), od = __shfl_sync(0xffffffffu, desc, lo), oe = __shfl_sync(0xffffffffu, excl, lo);
-        if (t < wtot) items[gbase + t] = make_uint2(oa, od | (t - oe));
+        const uint32_t on = __shfl_sync(0xffffffffu, ncont, lo);
+        if (t < wtot) {
+            const uint32_t g = t - oe, left = on - 4u * g;            // group index, contacts from this group on
+            items[gbase + t] = make_uint2(oa, od | g | (((left < 4u ? left : 4u) - 1u) << 5));
+        }
     }
 }
 
@@ -732,12 +745,23 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
     const int n_chunks = (G.Npad + SW_CHUNK - 1) / SW_CHUNK;
     const int n4 = G.Npad >> 2;
     uint32_t head = 0, tail = 0, e_head = 0, e_tail = 0, t_head = 0, t_tail = 0;
-    for (int chunk = blockIdx.x * SW_WARPS + warp; chunk < n_chunks; chunk += gridDim.x * SW_WARPS) {
+    const int stride = gridDim.x * SW_WARPS;
+    int chunk = blockIdx.x * SW_WARPS + warp;
+    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;          // software pipeline: the next chunk's words are in flight
+    if (chunk < n_chunks) {                              // while the current chunk's active agents are processed
+        const int i0 = ((chunk * SW_CHUNK) >> 2) + lane;
+        if (i0 < n4) n0 = __ldg(&hot4[i0]);
+        if (i0 + 32 < n4) n1 = __ldg(&hot4[i0 + 32]);
+    }
+    for (; chunk < n_chunks; chunk += stride) {
         const int a0 = chunk * SW_CHUNK;
-        const int i0 = (a0 >> 2) + lane, i1 = i0 + 32;
-        uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
-        if (i0 < n4) w0 = __ldg(&hot4[i0]);
-        if (i1 < n4) w1 = __ldg(&hot4[i1]);
+        const uint4 w0 = n0, w1 = n1;
+        n0 = make_uint4(0, 0, 0, 0); n1 = n0;
+        if (chunk + stride < n_chunks) {
+            const int i0 = (((chunk + stride) * SW_CHUNK) >> 2) + lane;
+            if (i0 < n4) n0 = __ldg(&hot4[i0]);
+            if (i0 + 32 < n4) n1 = __ldg(&hot4[i0 + 32]);
+        }
         const uint32_t hw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
         uint32_t act = 0;
 #pragma unroll
@@ -776,13 +800,52 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
 }
 
 // ---------------------------------------------------------------- k_expose
-// One thread per sampled contact: get_one_contact (main.pyx:1290-1304), get_person_from_age_range (:1525-1535),
-// person_expose / did_infect (:238-244, 908-934).
-__global__ void __launch_bounds__(256) k_expose(Eng G) {
+// Contacts.  One thread per group of four contact slots of one infector (they share one Philox block):
+// get_one_contact (main.pyx:1290-1304) picks the row, daily_contacts[place] is counted, and a coarse 8-bit filter
+// (thinning, see the oracle) decides whether the contact can transmit at all.  The few survivors go through a
+// warp-private shared-memory ring and are finished on dense warps: get_person_from_age_range (:1525-1535),
+// person_expose / did_infect (:238-244, 908-934), atomicMin on the target's conflict slot.
+#define EX_THREADS 256
+#define EX_WARPS (EX_THREADS / 32)
+#define EX_RCAP 256
+
+__device__ __forceinline__ void expose_survivors(const Eng &G, int r, RepCtr *c, const DevTable *tb, const uint2 *items, const uint32_t *sus,
+                                                 Attempt *succ, const uint32_t *ri, const uint32_t *rx, uint32_t head, uint32_t m, int lane) {
+    if ((uint32_t)lane >= m) return;
+    const size_t base = (size_t)r * G.Npad;
+    const uint2 it = items[ri[(head + lane) & (EX_RCAP - 1)]];
+    const uint32_t info = rx[(head + lane) & (EX_RCAP - 1)];
+    const uint32_t slot = info & 127u, row = (info >> 7) & 127u, kq = info >> 14;
+    const uint32_t a = it.x, age = (it.y >> 7) & 127u, dayidx = (it.y >> 14) & 31u, var = (it.y >> 20) & 3u;
+    const rb_variant *v = &G.variants[var];
+    float si = v->iot[dayidx];
+    if ((it.y >> 19) & 1u) si = si * v->p_asymptomatic_infection;
+    const u32x4 y = philox(c->seed, a, (uint32_t)c->day, PU_CONTACT2 | (slot << 8), 0);
+    const uint32_t t = (uint32_t)tb->start[age][row] + y.x % (uint32_t)tb->size[age][row];
+    // person_expose (main.pyx:238-244): only a SUSCEPTIBLE target can be infected; the 1-bit-per-agent map keeps
+    // this random gather inside L2 instead of pulling a 32-byte DRAM sector per contact
+    if (!((__ldg(&sus[t >> 5]) >> (t & 31)) & 1u)) return;
+    const int tage = tb->susc_uniform[age][row] ? (int)tb->lo_age[age][row]
+                                                : age_in_band(G, (int32_t)t, tb->lo_age[age][row], tb->hi_age[age][row]);
+    const float pr = (si * v->tab[RB_T_SUSCEPTIBILITY][tage]) * v->infectiousness_multiplier;
+    if (!(((double)y.y * (1.0 / 4294967296.0)) * (double)kq < (double)pr * 256.0)) return;
+    const float mp = tb->mask_p[age][row];
+    if (mp != 0.0f) {
+        const float ma = mp * v->p_mask_protects_others, mb = mp * v->p_mask_protects_wearer;
+        const float pm = (ma + mb) - ma * mb;
+        if (chance((double)y.z * (1.0 / 4294967296.0), pm)) return;
+    }
+    const unsigned long long key = ((unsigned long long)sweep_pos(G, c, a) << 7) | slot;
+    const uint32_t idx = atomicAdd(&c->n_succ, 1u);
+    if (idx < G.cap_succ) { succ[idx].cand = t; succ[idx].parent = a; succ[idx].key = key; atomicMin(&G.winner[base + t], key); }
+    else set_problem(c, RB_OTHER_FAILURE);
+}
+
+__global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
     __shared__ int s_place[RB_N_PLACES];
+    __shared__ uint32_t s_ri[EX_WARPS][EX_RCAP], s_rx[EX_WARPS][EX_RCAP];
     const int r = blockIdx.y;
     RepCtr *c = &G.ctr[r];
-    const size_t base = (size_t)r * G.Npad;
     const DevTable *tb = G.tables[c->epoch];
     const uint32_t n = min(c->n_items, G.cap_items);
     if (blockIdx.x * blockDim.x >= n) return;
@@ -792,42 +855,62 @@ __global__ void __launch_bounds__(256) k_expose(Eng G) {
     Attempt *succ = G.succ + (size_t)r * G.cap_succ;
     const uint32_t *sus = G.sus + (size_t)r * G.sus_words;
     const uint32_t day = (uint32_t)c->day;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint2 it = items[i];
-        uint32_t a = it.x, slot = it.y & 127u, age = (it.y >> 7) & 127u, dayidx = (it.y >> 14) & 31u;
-        bool asym = (it.y >> 19) & 1u; uint32_t var = (it.y >> 20) & 3u;
-        // one Philox block per contact: word x -> row, y -> person within the band, z -> transmission, w -> mask
-        u32x4 x = philox(c->seed, a, day, PU_CONTACT | (slot << 8), 0);
-        const double u = (double)x.x * (1.0 / 4294967296.0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *ri = s_ri[warp], *rx = s_rx[warp];
+    uint32_t head = 0, tail = 0;
+    uint32_t places = 0;                 // this thread's per-place counters, 5 bits each, flushed every 7 iterations
+    int since_flush = 0;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + warp * 32; i0 < n; i0 += gridDim.x * blockDim.x) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < n;
+        uint32_t words[4] = {0, 0, 0, 0}, ncnt = 0, age = 0, grp = 0;
+        int kq = 0;
+        if (valid) {
+            const uint2 it = items[i];
+            grp = it.y & 31u; ncnt = ((it.y >> 5) & 3u) + 1u; age = (it.y >> 7) & 127u;
+            const rb_variant *v = &G.variants[(it.y >> 20) & 3u];
+            float si = v->iot[(it.y >> 14) & 31u];
+            if ((it.y >> 19) & 1u) si = si * v->p_asymptomatic_infection;
+            const float p_upper = (si * v->reserved[0]) * v->infectiousness_multiplier;
+            kq = (int)(p_upper * 256.0f) + 1;
+            if (kq > 256) kq = 256;
+            const u32x4 x = philox(c->seed, it.x, day, PU_CONTACT | (grp << 8), 0);
+            words[0] = x.x; words[1] = x.y; words[2] = x.z; words[3] = x.w;
+        }
         const int nrows = tb->n_rows[age];
         const double *cum = tb->cum_p[age];
-        // get_one_contact (main.pyx:1290-1304) is a linear scan for the first row with u < cum_p; rows below
-        // guide[u's top byte] cannot match, so the scan starts there and ends after ~1 step
-        int row = tb->guide[age][x.x >> 24];
-        while (row < nrows - 1 && !(u < cum[row])) row++;      // last row on overrun: the reference fails there (p ~ 1e-15)
-        uint32_t t = (uint32_t)tb->start[age][row] + x.y % (uint32_t)tb->size[age][row];
-        atomicAdd(&s_place[tb->place[age][row]], 1);
-        // person_expose (main.pyx:238-244): only a SUSCEPTIBLE target can be infected; the 1-bit-per-agent map
-        // keeps this random gather inside L2 instead of pulling a 32-byte DRAM sector per contact
-        if (!((__ldg(&sus[t >> 5]) >> (t & 31)) & 1u)) continue;
-        const rb_variant *v = &G.variants[var];
-        float si = v->iot[dayidx];
-        if (asym) si = si * v->p_asymptomatic_infection;
-        int tage = tb->susc_uniform[age][row] ? (int)tb->lo_age[age][row]
-                                              : age_in_band(G, (int32_t)t, tb->lo_age[age][row], tb->hi_age[age][row]);
-        float pr = (si * v->tab[RB_T_SUSCEPTIBILITY][tage]) * v->infectiousness_multiplier;
-        if (!chance((double)x.z * (1.0 / 4294967296.0), pr)) continue;
-        float mp = tb->mask_p[age][row];
-        if (mp != 0.0f) {
-            float ma = mp * v->p_mask_protects_others, mb = mp * v->p_mask_protects_wearer;
-            float pm = (ma + mb) - ma * mb;
-            if (chance((double)x.w * (1.0 / 4294967296.0), pm)) continue;
+#pragma unroll
+        for (uint32_t w = 0; w < 4; w++) {
+            bool pass = false;
+            uint32_t row = 0;
+            if (w < ncnt) {
+                const uint32_t word = words[w];
+                const double u = (double)(word >> 8) * (1.0 / 16777216.0);
+                // linear scan for the first row with u < cum_p; rows below guide[u's top byte] cannot match
+                row = tb->guide[age][word >> 24];
+                while ((int)row < nrows - 1 && !(u < cum[row])) row++;   // last row on overrun: the reference fails there (p ~ 1e-15)
+                places += 1u << (5 * tb->place[age][row]);               // daily_contacts[place]++ (main.pyx:1571)
+                pass = (int)(word & 255u) < kq;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (pass) {
+                const uint32_t p = (tail + __popc(m & ((1u << lane) - 1u))) & (EX_RCAP - 1);
+                ri[p] = i; rx[p] = (grp * 4u + w) | (row << 7) | ((uint32_t)kq << 14);
+            }
+            tail += __popc(m);
         }
-        unsigned long long key = ((unsigned long long)sweep_pos(G, c, a) << 7) | slot;
-        uint32_t idx = atomicAdd(&c->n_succ, 1u);
-        if (idx < G.cap_succ) { succ[idx].cand = t; succ[idx].parent = a; succ[idx].key = key; atomicMin(&G.winner[base + t], key); }
-        else set_problem(c, RB_OTHER_FAILURE);
+        __syncwarp();
+        while (tail - head >= 32) { expose_survivors(G, r, c, tb, items, sus, succ, ri, rx, head, 32, lane); head += 32; }
+        __syncwarp();
+        if (++since_flush == 7) {        // 7 iterations x 4 contacts = 28 < 32 fits the 5-bit fields
+#pragma unroll
+            for (int pl = 0; pl < RB_N_PLACES; pl++) { const uint32_t k = (places >> (5 * pl)) & 31u; if (k) atomicAdd(&s_place[pl], (int)k); }
+            places = 0; since_flush = 0;
+        }
     }
+    if (tail != head) expose_survivors(G, r, c, tb, items, sus, succ, ri, rx, head, tail - head, lane);
+#pragma unroll
+    for (int pl = 0; pl < RB_N_PLACES; pl++) { const uint32_t k = (places >> (5 * pl)) & 31u; if (k) atomicAdd(&s_place[pl], (int)k); }
     __syncthreads();
     if (threadIdx.x < RB_N_PLACES && s_place[threadIdx.x]) atomicAdd(&c->daily_contacts[threadIdx.x], s_place[threadIdx.x]);
 }
@@ -1132,10 +1215,20 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     CK(cudaMemset(e->d_tables, 0, sizeof(DevTable *) * e->n_table_slots));
     G.tables = e->d_tables;
     e->tables.assign(e->n_table_slots, nullptr);
-    rb_variant *dv; int32_t *d_as, *d_ga, *d_ilo, *d_ihi; float *d_icum;
+    rb_variant *dv; int32_t *d_as, *d_ga, *d_ilo, *d_ihi; float *d_icum; uint8_t *d_ab;
     if (dalloc(e, &dv, (size_t)cfg->n_variants) || dalloc(e, &d_as, (size_t)cfg->n_ages + 1) || dalloc(e, &d_ga, (size_t)cfg->n_ages) ||
         dalloc(e, &d_ilo, (size_t)RB_MAX_IMPORT_CLASSES) || dalloc(e, &d_ihi, (size_t)RB_MAX_IMPORT_CLASSES) ||
-        dalloc(e, &d_icum, (size_t)RB_MAX_IMPORT_CLASSES)) { rb_destroy(e); return 1; }
+        dalloc(e, &d_icum, (size_t)RB_MAX_IMPORT_CLASSES) || dalloc(e, &d_ab, (size_t)(G.Npad >> 10) + 2)) { rb_destroy(e); return 1; }
+    {
+        std::vector<uint8_t> ab((size_t)(G.Npad >> 10) + 2);
+        int age = 0;
+        for (size_t b = 0; b < ab.size(); b++) {
+            int64_t a = (int64_t)b << 10; if (a > N - 1) a = N - 1;
+            while (age < cfg->n_ages - 1 && e->age_start[age + 1] <= a) age++;
+            ab[b] = (uint8_t)age;
+        }
+        CK(cudaMemcpy(d_ab, ab.data(), ab.size(), cudaMemcpyHostToDevice));
+    }
     e->h_variants.assign(variants, variants + cfg->n_variants);
     CK(cudaMemcpy(dv, variants, sizeof(rb_variant) * cfg->n_variants, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_as, e->age_start.data(), sizeof(int32_t) * (cfg->n_ages + 1), cudaMemcpyHostToDevice));
@@ -1143,7 +1236,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     CK(cudaMemcpy(d_ilo, import_lo, sizeof(int32_t) * cfg->n_import_classes, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_ihi, import_hi, sizeof(int32_t) * cfg->n_import_classes, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_icum, import_cum, sizeof(float) * cfg->n_import_classes, cudaMemcpyHostToDevice));
-    G.variants = dv; G.age_start = d_as; G.group_of_age = d_ga; G.import_lo = d_ilo; G.import_hi = d_ihi; G.import_cum = d_icum;
+    G.age_blk = d_ab; G.variants = dv; G.age_start = d_as; G.group_of_age = d_ga; G.import_lo = d_ilo; G.import_hi = d_ihi; G.import_cum = d_icum;
     e->age_counts.assign(age_counts, age_counts + cfg->n_ages);
     if (init_counters(e, cfg->seed)) { rb_destroy(e); return 1; }
     CK(cudaMemset(G.stats, 0, sizeof(int32_t) * (size_t)R * (cfg->max_days + 1) * G.row_len));
@@ -1200,6 +1293,13 @@ extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *
         }
     }
     for (int age = 0; age < e->cfg.n_ages; age++)
+        for (int cls = 0; cls < 2; cls++)
+            for (int b = 0; b < 64; b++) {
+                int limit = cls ? 5 : 100, k = 0;
+                while (k < limit && !(h->ncdf[age][cls][k] > (double)b / 64.0)) k++;
+                h->nguide[age][cls][b] = (uint8_t)k;
+            }
+    for (int age = 0; age < e->cfg.n_ages; age++)
         for (int b = 0; b < 256; b++) {
             int i = 0;
             while (i < n_rows[age] - 1 && !(h->cum_p[age][i] > (double)b / 256.0)) i++;
@@ -1226,7 +1326,7 @@ extern "C" int rb_set_schedule(rb_engine *e, int32_t day0, int32_t n, const rb_d
 static void launch_segment(rb_engine *e, cudaStream_t st) {
     const Eng &G = e->G;
     k_sweep<<<dim3(e->sweep_blocks, G.R), SW_THREADS, 0, st>>>(G);
-    k_expose<<<dim3(e->list_blocks, G.R), 256, 0, st>>>(G);
+    k_expose<<<dim3(e->list_blocks, G.R), EX_THREADS, 0, st>>>(G);
     k_resolve<<<dim3(e->list_blocks, G.R), 256, 0, st>>>(G);
     k_between<<<G.R, PRE_THREADS, 0, st>>>(G);
 }

@@ -124,6 +124,8 @@ def make_variant(params, n_ages):
         arr = _greatest_lte_table([tuple(x) for x in pairs], n_ages)
         for age in range(_abi.RB_MAX_AGES):
             v.tab[t][age] = arr[age]
+        if t == _abi.T_SUSCEPTIBILITY:
+            v.reserved[0] = float(arr[:n_ages].max())      # upper bound used by the contact kernel's coarse filter
     return v
 
 
