@@ -88,12 +88,13 @@ struct RepCtr {
     uint32_t seed, start;
     uint32_t fkey[4];
     uint32_t n_items, n_succ, n_events, n_queue, n_newq, qsel;
-    uint32_t n_l0, n_l1, n_edges, pad0;
+    uint32_t n_l0, n_l1, n_edges, stream_mode;   // stream_mode: today's sweep streams the packed words instead of the activity bitmap
     int32_t vacc_cursor[RB_MAX_VACC];
     int32_t pad[8];
 };
 
 struct Eng {
+    int32_t dbg;                                   // measurement aid: 1/2/3 skip a sweep stage (timing experiments only)
     int32_t N, Npad, n_ages, n_groups, n_variants, R, max_days, row_len, n_import_classes, fhalf;
     uint32_t cap_items, cap_succ, cap_events, cap_queue;
     uint32_t *hot, *cold, *inf_key;
@@ -102,6 +103,7 @@ struct Eng {
     unsigned long long *winner;
     uint32_t *sus;                                 // [R][sus_words] 1 bit per agent: still SUSCEPTIBLE (L2-resident gather target)
     int32_t sus_words;
+    uint32_t *act;                                 // [R][sus_words] 1 bit per agent: has work in today's sweep (infected, or removed and not yet counted)
     uint2 *items;
     Attempt *succ;
     unsigned long long *ev_key; int32_t *ev_agent;
@@ -182,6 +184,7 @@ __device__ void device_infect(const Eng &G, int r, RepCtr *c, int32_t t, int32_t
     if (c->testing_mode == RB_ALL_WITH_SYMPTOMS_CT) nh |= H_LIST;
     G.hot[base + t] = nh;
     atomicAnd(&G.sus[(size_t)r * G.sus_words + (t >> 5)], ~(1u << (t & 31)));
+    atomicOr(&G.act[(size_t)r * G.sus_words + (t >> 5)], 1u << (t & 31));
     count_add(c, RB_A_SUSCEPTIBLE, age, -1);
     count_add(c, RB_A_INFECTED, age, 1);
     count_add(c, RB_A_ALL_INFECTED, age, 1);
@@ -527,6 +530,10 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
         u32x4 x = philox(c->seed, 0u, (uint32_t)day, PU_START, 0);     // _iterate_people, main.pyx:1988
         c->start = x.x % (uint32_t)G.N;
         c->n_items = 0; c->n_succ = 0; c->n_events = 0;
+        // dense days (> 1/24 of the agents infected) stream the packed words, sparse days walk the activity bitmap
+        int infected = 0;
+        for (int age = 0; age < G.n_ages; age++) infected += c->counts[RB_A_INFECTED][age];
+        c->stream_mode = (long long)infected * 24 > (long long)G.N ? 1u : 0u;
     }
 }
 
@@ -549,7 +556,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
 #define SW_RCAP 64
 
 struct WarpRings {
-    uint32_t qi[SW_QCAP], qw[SW_QCAP];      // ring A: agent index, packed word
+    uint32_t qi[SW_QCAP];                   // ring A: agent index
     uint32_t ea[SW_RCAP], ed[SW_RCAP];      // ring E: agent index, contact descriptor
     uint32_t ta[SW_RCAP], tw[SW_RCAP];      // ring T: agent index, packed word (day counters already advanced)
 };
@@ -703,12 +710,13 @@ __device__ __forceinline__ void stage_active(const Eng &G, int r, RepCtr *c, War
     uint32_t a = 0, h = 0, desc = 0;
     if ((uint32_t)lane < m) {
         a = W.qi[(head + lane) & (SW_QCAP - 1)];
-        h = W.qw[(head + lane) & (SW_QCAP - 1)];
+        h = G.hot[base + a];               // the only per-agent gather of the sweep: ~3 % of the agents on an average day
         const uint32_t st = H_STATE(h);
         if (st >= RB_RECOVERED) {          // R bookkeeping, main.pyx:1969-1972 (only agents not yet included reach here)
             atomicAdd(&c->total_infectors, 1);
             atomicAdd(&c->total_infections, (int)(G.cold[base + a] & 0xffffu));
             G.hot[base + a] = h | H_INCL;
+            atomicAnd(&G.act[(size_t)r * G.sus_words + (a >> 5)], ~(1u << (a & 31)));   // nothing left to do for this agent
         } else if (h & H_FRESH) {          // infected today before the sweep: wait until tomorrow, main.pyx:402-403
             G.hot[base + a] = h & ~H_FRESH;
         } else {
@@ -738,58 +746,86 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
     const DevTable *tb = G.tables[c->epoch];
-    const uint4 *hot4 = reinterpret_cast<const uint4 *>(G.hot + base);
+    const uint4 *act4 = reinterpret_cast<const uint4 *>(G.act + (size_t)r * G.sus_words);
     uint2 *items = G.items + (size_t)r * G.cap_items;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpRings &W = s_rings[warp];
-    const int n_chunks = (G.Npad + SW_CHUNK - 1) / SW_CHUNK;
-    const int n4 = G.Npad >> 2;
+    // One bit per agent says whether the sweep has anything to do for it (infected, or removed and not yet counted in
+    // R), so the pass over all N agents reads 1/32 of the packed state -- an L2-resident bitmap -- and only the
+    // active agents' words are gathered.  A warp step covers 32 lanes x 128 agents.
+    const int n_vec = G.sus_words >> 2;
     uint32_t head = 0, tail = 0, e_head = 0, e_tail = 0, t_head = 0, t_tail = 0;
-    const int stride = gridDim.x * SW_WARPS;
-    int chunk = blockIdx.x * SW_WARPS + warp;
-    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;          // software pipeline: the next chunk's words are in flight
-    if (chunk < n_chunks) {                              // while the current chunk's active agents are processed
-        const int i0 = ((chunk * SW_CHUNK) >> 2) + lane;
-        if (i0 < n4) n0 = __ldg(&hot4[i0]);
-        if (i0 + 32 < n4) n1 = __ldg(&hot4[i0 + 32]);
-    }
-    for (; chunk < n_chunks; chunk += stride) {
-        const int a0 = chunk * SW_CHUNK;
-        const uint4 w0 = n0, w1 = n1;
-        n0 = make_uint4(0, 0, 0, 0); n1 = n0;
-        if (chunk + stride < n_chunks) {
-            const int i0 = (((chunk + stride) * SW_CHUNK) >> 2) + lane;
-            if (i0 < n4) n0 = __ldg(&hot4[i0]);
-            if (i0 + 32 < n4) n1 = __ldg(&hot4[i0 + 32]);
-        }
-        const uint32_t hw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        uint32_t act = 0;
+    if (c->stream_mode) {
+        // dense day: coalesced 16-byte loads of the packed words themselves, 256 agents per warp step; the queued
+        // agents' words are re-read in stage 1 from L1
+        const uint4 *hot4 = reinterpret_cast<const uint4 *>(G.hot + base);
+        const int n_chunks = (G.Npad + SW_CHUNK - 1) / SW_CHUNK, n4 = G.Npad >> 2;
+        for (int chunk = blockIdx.x * SW_WARPS + warp; chunk < n_chunks; chunk += gridDim.x * SW_WARPS) {
+            const int a0 = chunk * SW_CHUNK;
+            const int i0 = (a0 >> 2) + lane, i1 = i0 + 32;
+            uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
+            if (i0 < n4) w0 = hot4[i0];
+            if (i1 < n4) w1 = hot4[i1];
+            const uint32_t hw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            uint32_t act = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            uint32_t st = H_STATE(hw[j]);
-            if (st != RB_SUSCEPTIBLE && !(st >= RB_RECOVERED && (hw[j] & H_INCL))) act |= 1u << j;
-        }
-        if (!__any_sync(0xffffffffu, act != 0)) continue;
-        uint32_t mine = __popc(act), incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t p = tail + incl - mine;
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (act & (1u << j)) {
-                W.qi[p & (SW_QCAP - 1)] = (uint32_t)(a0 + (j < 4 ? lane * 4 + j : 128 + lane * 4 + (j - 4)));
-                W.qw[p & (SW_QCAP - 1)] = hw[j];
-                p++;
+            for (int j = 0; j < 8; j++) {
+                uint32_t st = H_STATE(hw[j]);
+                if (st != RB_SUSCEPTIBLE && !(st >= RB_RECOVERED && (hw[j] & H_INCL))) act |= 1u << j;
             }
-        tail += tot;
-        __syncwarp();
-        while (tail - head >= 32) {
-            stage_active(G, r, c, W, head, 32, e_tail, t_tail, lane); head += 32;
+            if (!__any_sync(0xffffffffu, act != 0)) continue;
+            uint32_t mine = __popc(act), incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t p = tail + incl - mine;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (act & (1u << j)) { W.qi[p & (SW_QCAP - 1)] = (uint32_t)(a0 + (j < 4 ? lane * 4 + j : 128 + lane * 4 + (j - 4))); p++; }
+            tail += tot;
             __syncwarp();
-            if (e_tail - e_head >= 32) { stage_expose(G, c, tb, W, e_head, 32, items, lane); e_head += 32; }
-            if (t_tail - t_head >= 32) { stage_transition(G, r, c, W, t_head, 32, lane); t_head += 32; }
-            __syncwarp();
+            while (tail - head >= 32) {
+                stage_active(G, r, c, W, head, 32, e_tail, t_tail, lane); head += 32;
+                __syncwarp();
+                if (e_tail - e_head >= 32) { stage_expose(G, c, tb, W, e_head, 32, items, lane); e_head += 32; }
+                if (t_tail - t_head >= 32) { stage_transition(G, r, c, W, t_head, 32, lane); t_head += 32; }
+                __syncwarp();
+            }
+        }
+    } else
+    for (int v0 = (blockIdx.x * SW_WARPS + warp) * 32; v0 < n_vec; v0 += gridDim.x * SW_WARPS * 32) {
+        const int vi = v0 + lane;
+        uint4 bits = make_uint4(0, 0, 0, 0);
+        if (vi < n_vec) bits = __ldg(&act4[vi]);
+        if (!__any_sync(0xffffffffu, (bits.x | bits.y | bits.z | bits.w) != 0u)) continue;
+        uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t w = bw[q];
+            const uint32_t abase = (uint32_t)vi * 128u + (uint32_t)q * 32u;
+            while (__any_sync(0xffffffffu, w != 0u)) {
+                // every lane queues up to 8 of its set bits per round: at most 256 pushes, the ring holds 512
+                uint32_t mine = min(__popc(w), 8), incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                uint32_t p = tail + incl - mine;
+                for (uint32_t k = 0; k < mine; k++) {
+                    W.qi[p & (SW_QCAP - 1)] = abase + (uint32_t)(__ffs(w) - 1);
+                    w &= w - 1u;
+                    p++;
+                }
+                tail += tot;
+                __syncwarp();
+                while (tail - head >= 32) {
+                    if (G.dbg == 3) { head += 32; continue; }
+                    stage_active(G, r, c, W, head, 32, e_tail, t_tail, lane); head += 32;
+                    __syncwarp();
+                    if (e_tail - e_head >= 32) { if (G.dbg != 1) stage_expose(G, c, tb, W, e_head, 32, items, lane); e_head += 32; }
+                    if (t_tail - t_head >= 32) { if (G.dbg != 2) stage_transition(G, r, c, W, t_head, 32, lane); t_head += 32; }
+                    __syncwarp();
+                }
+            }
         }
     }
     // drain: whatever is left in ring A, then rings E and T (at most two partial batches each)
@@ -1056,6 +1092,7 @@ __global__ void k_init(Eng G) {
         int first = w * 32;
         uint32_t m = first + 32 <= G.N ? 0xffffffffu : (first >= G.N ? 0u : ((1u << (G.N - first)) - 1u));
         G.sus[(size_t)r * G.sus_words + w] = m;
+        G.act[(size_t)r * G.sus_words + w] = 0u;
     }
 }
 
@@ -1200,10 +1237,10 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     G.cap_events = pow2_at_least((uint64_t)N / 16 + 2048);
     G.cap_queue = pow2_at_least((uint64_t)N / 8 + 2048);
     const size_t RN = (size_t)R * G.Npad;
-    G.sus_words = (G.Npad + 31) / 32 + 32;
+    G.sus_words = ((G.Npad + 31) / 32 + 32 + 3) & ~3;     // multiple of 4 words: the sweep reads the bitmaps 16 bytes at a time
     if (dalloc(e, &G.hot, RN) || dalloc(e, &G.cold, RN) || dalloc(e, &G.inf_key, RN) || dalloc(e, &G.infector, RN) ||
         dalloc(e, &G.first_child, RN) || dalloc(e, &G.next_sib, RN) || dalloc(e, &G.vacc_day, RN) || dalloc(e, &G.winner, RN) ||
-        dalloc(e, &G.sus, (size_t)R * ((G.Npad + 31) / 32 + 32)) || dalloc(e, &G.items, (size_t)R * G.cap_items) || dalloc(e, &G.succ, (size_t)R * G.cap_succ) ||
+        dalloc(e, &G.sus, (size_t)R * G.sus_words) || dalloc(e, &G.act, (size_t)R * G.sus_words) || dalloc(e, &G.items, (size_t)R * G.cap_items) || dalloc(e, &G.succ, (size_t)R * G.cap_succ) ||
         dalloc(e, &G.ev_key, (size_t)R * G.cap_events) || dalloc(e, &G.ev_agent, (size_t)R * G.cap_events) ||
         dalloc(e, &G.q_key, (size_t)R * 2 * G.cap_queue) || dalloc(e, &G.q_agent, (size_t)R * 2 * G.cap_queue) ||
         dalloc(e, &G.ctr, (size_t)R) || dalloc(e, &G.stats, (size_t)R * (cfg->max_days + 1) * G.row_len) ||
@@ -1244,7 +1281,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     // launch geometry: grid-stride kernels sized in multiples of the SM count
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     int sms = prop.multiProcessorCount;
-    int want = (G.Npad + SW_CHUNK * SW_WARPS - 1) / (SW_CHUNK * SW_WARPS);
+    int want = (G.sus_words / 4 + SW_WARPS * 32 - 1) / (SW_WARPS * 32);
     int per_rep = (sms * 8 + R - 1) / R; if (per_rep < 4) per_rep = 4;
     e->sweep_blocks = want < per_rep ? want : per_rep; if (e->sweep_blocks < 1) e->sweep_blocks = 1;
     e->list_blocks = (sms * 4 + R - 1) / R; if (e->list_blocks < 2) e->list_blocks = 2;
@@ -1411,6 +1448,7 @@ extern "C" int rb_sync(rb_engine *e) {
 }
 
 extern "C" int32_t rb_day(rb_engine *e) { return e->day; }
+extern "C" void rb_debug_flag(rb_engine *e, int32_t v) { e->G.dbg = v; }
 extern "C" int32_t rb_row_len(rb_engine *e) { return e->G.row_len; }
 extern "C" float rb_last_step_ms(rb_engine *e) { return e->last_ms; }
 extern "C" int64_t rb_launch_count(rb_engine *e) { return e->launches; }
