@@ -88,9 +88,13 @@ struct RepCtr {
     uint32_t seed, start;
     uint32_t fkey[4];
     uint32_t n_items, n_succ, n_events, n_queue, n_newq, qsel;
+    uint32_t n_queue_prev;                        // size of the queue drained yesterday (normalises tracing keys for sorting)
+    uint32_t any_vacc;                            // set once the first vaccination programme starts
     uint32_t n_l0, n_l1, n_edges, stream_mode;   // stream_mode: today's sweep streams the packed words instead of the activity bitmap
     int32_t vacc_cursor[RB_MAX_VACC];
-    int32_t pad[8];
+    int32_t pad[6];
+    long long dbg_t[16];                          // measurement aid: cycles spent per phase of the day-boundary kernel
+    long long dbg_last;
 };
 
 struct Eng {
@@ -161,25 +165,30 @@ __device__ __forceinline__ int symptom_severity(const rb_variant *v, int age, fl
 // (ignored when src < 0).  Severity and incubation use wild-type parameters (variant_idx is still 0 there).
 __device__ void device_infect(const Eng &G, int r, RepCtr *c, int32_t t, int32_t src, uint32_t src_h, int variant,
                               int slot, bool fresh) {
-    size_t base = (size_t)r * G.Npad;
-    int day = c->day;
-    int age = age_of(G, t);
+    const size_t base = (size_t)r * G.Npad;
+    const int day = c->day;
+    // the two atomics whose results are needed go first; the draws below hide their round trip
+    uint32_t old = 0; int32_t prev_child = -1;
+    if (src >= 0) {
+        old = atomicAdd(&G.cold[base + src], 1u);
+        prev_child = atomicExch(&G.first_child[base + src], t);
+    }
+    const int vd = c->any_vacc ? (int)G.vacc_day[base + t] : -1;     // nobody is vaccinated in most configurations
+    const int age = age_of(G, t);
     const rb_variant *v0 = &G.variants[0];
-    uint32_t h = G.hot[base + t];
-    int vd = G.vacc_day[base + t];
-    bool vacc_eff = vd >= 0 && (day - vd) > 14;
+    const bool vacc_eff = vd >= 0 && (day - vd) > 14;
     u32x4 x = philox(c->seed, (uint32_t)t, (uint32_t)day, PU_SEVERITY, 0);
-    int sev = symptom_severity(v0, age, u01f(x.x), vacc_eff);
-    int dl = clamp255(round_to_int(gamma_f(c->seed, (uint32_t)t, (uint32_t)day, PU_INCUB, v0->incubation_kappa, v0->incubation_theta)));
+    const int sev = symptom_severity(v0, age, u01f(x.x), vacc_eff);
+    const int dl = clamp255(round_to_int(gamma_f(c->seed, (uint32_t)t, (uint32_t)day, PU_INCUB, v0->incubation_kappa, v0->incubation_theta)));
     if (src >= 0) {
         variant = (int)H_VAR(src_h);
         G.infector[base + t] = src;
-        uint32_t old = atomicAdd(&G.cold[base + src], 1u) & 0xffffu;
-        if ((src_h & H_LIST) && old >= MAX_INFECTEES) set_problem(c, RB_TOO_MANY_INFECTEES);
+        if ((src_h & H_LIST) && (old & 0xffffu) >= MAX_INFECTEES) set_problem(c, RB_TOO_MANY_INFECTEES);
         G.inf_key[base + t] = ((uint32_t)day << 8) | (uint32_t)slot;
-        G.next_sib[base + t] = atomicExch(&G.first_child[base + src], t);
+        G.next_sib[base + t] = prev_child;
     }
-    uint32_t nh = (h & H_VACC) | RB_INCUBATION | ((uint32_t)sev << 3) | ((uint32_t)variant << 8) | ((uint32_t)dl << 14);
+    // a SUSCEPTIBLE agent's word carries nothing but the vaccinated flag, which vacc_day implies
+    uint32_t nh = (vd >= 0 ? H_VACC : 0u) | RB_INCUBATION | ((uint32_t)sev << 3) | ((uint32_t)variant << 8) | ((uint32_t)dl << 14);
     if (fresh) nh |= H_FRESH;
     if (c->testing_mode == RB_ALL_WITH_SYMPTOMS_CT) nh |= H_LIST;
     G.hot[base + t] = nh;
@@ -255,6 +264,61 @@ __device__ int block_scan_incl(int v, int *total, int *warp_sums) {
     return v + prefix;
 }
 
+// Order-preserving bucket function for the two kinds of sort keys: capacity events (sweep position << 2 | type) and
+// test-queue entries (contact-tracing attempt keys first, then QKEY_SWEEP | sweep position).  Sweep positions are a
+// keyed permutation, so buckets receive ~n/2048 elements each.
+#define SORT_BUCKETS 2048
+struct BucketMap { uint32_t n_agents, n_prev; int kind; };     // kind 0: events, 1: queue
+__device__ __forceinline__ uint32_t bucket_of(const BucketMap &bm, unsigned long long key) {
+    if (bm.kind == 0) return (uint32_t)(((key >> 2) * SORT_BUCKETS) / bm.n_agents);
+    if (key & QKEY_SWEEP) return SORT_BUCKETS / 2 + (uint32_t)(((key & 0xffffffffull) * (SORT_BUCKETS / 2)) / bm.n_agents);
+    unsigned long long i = key >> 14;                          // queue rank of the tracer, < n_prev
+    return (uint32_t)((i * (SORT_BUCKETS / 2)) / (bm.n_prev ? bm.n_prev : 1u));
+}
+
+// Ascending sort of n (key, val) pairs with distinct keys by one CTA: counting sort into SORT_BUCKETS order-preserving
+// buckets (shared-memory histogram + scan), then each bucket is put in order by one thread.  O(n) for the uniformly
+// spread keys of this engine; `scratch` needs 2 n entries.  Returns false if the scratch area is too small.
+__device__ bool block_bucket_sort(unsigned long long *keys, int32_t *vals, uint32_t n, Attempt *scratch, uint32_t scratch_cap,
+                                  const BucketMap &bm, int32_t *cnt /* shared [SORT_BUCKETS] */, int *warp_sums) {
+    if (2ull * n > scratch_cap) return false;
+    const int tid = threadIdx.x;
+    for (int b = tid; b < SORT_BUCKETS; b += blockDim.x) cnt[b] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += blockDim.x) {
+        const unsigned long long k = keys[i];
+        const uint32_t b = min(bucket_of(bm, k), (uint32_t)SORT_BUCKETS - 1u);
+        const uint32_t slot = (uint32_t)atomicAdd(&cnt[b], 1);
+        scratch[i].key = k; scratch[i].cand = (uint32_t)vals[i]; scratch[i].parent = b | (slot << 11);
+    }
+    __syncthreads();
+    // exclusive scan of the bucket counts: two buckets per thread
+    const int c0 = tid * 2 < SORT_BUCKETS ? cnt[tid * 2] : 0, c1 = tid * 2 + 1 < SORT_BUCKETS ? cnt[tid * 2 + 1] : 0;
+    int total;
+    const int incl = block_scan_incl(c0 + c1, &total, warp_sums);
+    if (tid * 2 < SORT_BUCKETS) { cnt[tid * 2] = incl - c0 - c1; cnt[tid * 2 + 1] = incl - c1; }
+    __syncthreads();
+    Attempt *out = scratch + n;
+    for (uint32_t i = tid; i < n; i += blockDim.x) {
+        const Attempt e = scratch[i];
+        out[cnt[e.parent & (SORT_BUCKETS - 1)] + (e.parent >> 11)] = e;
+    }
+    __syncthreads();
+    for (int b = tid; b < SORT_BUCKETS; b += blockDim.x) {      // insertion sort inside each bucket (usually 0-2 elements)
+        const uint32_t lo = (uint32_t)cnt[b], hi = b + 1 < SORT_BUCKETS ? (uint32_t)cnt[b + 1] : n;
+        for (uint32_t i = lo + 1; i < hi; i++) {
+            const Attempt e = out[i];
+            uint32_t j = i;
+            while (j > lo && out[j - 1].key > e.key) { out[j] = out[j - 1]; j--; }
+            out[j] = e;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += blockDim.x) { keys[i] = out[i].key; vals[i] = (int32_t)out[i].cand; }
+    __syncthreads();
+    return true;
+}
+
 // Context.generate_state, main.pyx:1813-1857: fold per-age counters into age groups + scalars.
 __device__ void write_stats_row(const Eng &G, int r, RepCtr *c, int32_t *srow /* shared, >= row_len */) {
     int day = c->day;
@@ -281,24 +345,47 @@ __device__ void write_stats_row(const Eng &G, int r, RepCtr *c, int32_t *srow /*
     __syncthreads();
 }
 
-// Population.infect_people + get_import_infection_person, main.pyx:1632-1665 (sequential: a person picked by an
-// earlier import of the same day is no longer SUSCEPTIBLE for a later one).  Run by one thread.
-__device__ void import_infections(const Eng &G, int r, RepCtr *c, int count, int variant, int *ordinal) {
-    size_t base = (size_t)r * G.Npad;
-    for (int i = 0; i < count; i++) {
-        uint32_t ord = (uint32_t)(*ordinal)++;
-        int32_t found = -1;
-        for (uint32_t t = 0; t < 10; t++) {
+// Population.infect_people + get_import_infection_person, main.pyx:1632-1665.  Sequential semantics: import j takes
+// the first of its (up to 10) draws that is SUSCEPTIBLE and was not taken by an earlier import of the same day.
+// All draws of up to IMP_CHUNK imports are evaluated in parallel, one thread settles the order-dependent choice from
+// shared memory, then the chosen people are infected in parallel.  Called by the whole CTA.
+#define IMP_CHUNK 96
+__device__ void import_infections(const Eng &G, int r, RepCtr *c, int count, int variant, int *ordinal, int32_t *cand /*[IMP_CHUNK*10]*/,
+                                  int32_t *chosen /*[IMP_CHUNK]*/) {
+    const size_t base = (size_t)r * G.Npad;
+    const int tid = threadIdx.x;
+    for (int first = 0; first < count; first += IMP_CHUNK) {
+        const int m = min(IMP_CHUNK, count - first);
+        __syncthreads();
+        if (tid < m * 10) {
+            const uint32_t ord = (uint32_t)(*ordinal + first + tid / 10), t = (uint32_t)(tid % 10);
             u32x4 x = philox(c->seed, ord, (uint32_t)c->day, PU_IMPORT | (t << 8), 0);
             float p = u01f(x.x);
             int k = G.n_import_classes - 1;
             for (int j = 0; j < G.n_import_classes; j++) if (p <= G.import_cum[j]) { k = j; break; }
             int32_t s = G.age_start[G.import_lo[k]], en = G.age_start[G.import_hi[k] + 1];
             int32_t pi = s + (int32_t)(x.y % (uint32_t)(en - s));
-            if (H_STATE(G.hot[base + pi]) == RB_SUSCEPTIBLE) { found = pi; break; }
+            cand[tid] = H_STATE(G.hot[base + pi]) == RB_SUSCEPTIBLE ? pi : -1;
         }
-        if (found >= 0) device_infect(G, r, c, found, -1, 0u, variant, 0, true);
+        __syncthreads();
+        if (tid == 0) {
+            for (int j = 0; j < m; j++) {
+                int32_t found = -1;
+                for (int t = 0; t < 10 && found < 0; t++) {
+                    int32_t pi = cand[j * 10 + t];
+                    if (pi < 0) continue;
+                    bool taken = false;
+                    for (int q = 0; q < j; q++) if (chosen[q] == pi) { taken = true; break; }
+                    if (!taken) found = pi;
+                }
+                chosen[j] = found;
+            }
+        }
+        __syncthreads();
+        if (tid < m && chosen[tid] >= 0) device_infect(G, r, c, chosen[tid], -1, 0u, variant, 0, true);
     }
+    __syncthreads();
+    *ordinal += count;
 }
 
 // Candidates a tracer reaches (perform_contact_tracing, main.pyx:495-512): slot 0 = its infector, slots 1.. =
@@ -328,6 +415,7 @@ __device__ __forceinline__ bool trace_eligible(uint32_t h) {   // queue_for_test
     return H_STATE(h) != RB_DEAD && !(h & (H_DET | H_QUEUED));
 }
 
+#define TS(k) do { if (G.dbg == 9 && threadIdx.x == 0) { long long now_ = clock64(); c->dbg_t[k] += now_ - c->dbg_last; c->dbg_last = now_; } } while (0)
 // ---------------------------------------------------------------- day boundary (1 CTA per replica)
 struct MP { int a, b; };
 struct SmemSmall {
@@ -349,7 +437,9 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
     const rb_day_params *dp = &G.sched[day];
     const int tid = threadIdx.x;
 
+    if (G.dbg == 9 && threadIdx.x == 0) c->dbg_last = clock64();
     write_stats_row(G, r, c, srow);
+    TS(0);
 
     // apply_intervention effects dated today (main.pyx:1880-1960), then Population.init_day (:1687-1699)
     if (tid == 0) {
@@ -358,23 +448,22 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
         c->p_successful_tracing = dp->p_successful_tracing;
         c->beds += dp->beds_delta; c->avail_beds += dp->beds_delta;
         c->icu += dp->icu_delta; c->avail_icu += dp->icu_delta;
-        int ordinal = 0;
-        for (int i = 0; i < dp->n_imports; i++) import_infections(G, r, c, dp->import_amount[i], dp->import_variant[i], &ordinal);
-        sh_i[0] = ordinal;
     }
+    __syncthreads();
+    int ordinal = 0;       // uniform across the CTA
+    for (int i = 0; i < dp->n_imports; i++)
+        import_infections(G, r, c, dp->import_amount[i], dp->import_variant[i], &ordinal, (int32_t *)sk, sv);
     __syncthreads();
     for (int i = tid; i < G.n_ages; i += blockDim.x) { c->counts[RB_A_NEW_INFECTIONS][i] = 0; c->counts[RB_A_DETECTED][i] = 0; }
     if (tid < RB_N_PLACES) c->daily_contacts[tid] = 0;
     if (tid < RB_MAX_VARIANTS) c->by_variant[tid] = 0;
     __syncthreads();
-    if (tid == 0) {
-        c->epoch = dp->table_epoch;
-        int ordinal = sh_i[0];
-        for (int v = 0; v < G.n_variants; v++) if (dp->trickle[v]) import_infections(G, r, c, dp->trickle[v], v, &ordinal);
-        c->total_infectors = 0; c->total_infections = 0; c->exposed_per_day = 0;
-    }
+    if (tid == 0) { c->epoch = dp->table_epoch; c->total_infectors = 0; c->total_infections = 0; c->exposed_per_day = 0; }
+    for (int v = 0; v < G.n_variants; v++)
+        if (dp->trickle[v]) import_infections(G, r, c, dp->trickle[v], v, &ordinal, (int32_t *)sk, sv);
     __syncthreads();
 
+    TS(1);   // imports + init_day
     // HealthcareSystem.iterate (main.pyx:514-558): drain yesterday's queue
     const uint32_t cur = c->qsel, nxt = cur ^ 1u;
     unsigned long long *qk = G.q_key + ((size_t)r * 2 + cur) * G.cap_queue;
@@ -384,7 +473,11 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
     const uint32_t nq = c->n_queue;
     const bool ct = c->testing_mode == RB_ALL_WITH_SYMPTOMS_CT;
     if (tid == 0) { c->ct_cases = (int32_t)nq; c->n_newq = 0; c->n_l0 = 0; c->n_l1 = 0; c->n_edges = 0; }
-    if (ct) block_sort_pairs(qk, qa, nq, G.cap_queue, sk, sv);   // queue order only matters for tracing
+    if (ct && nq > 1) {                                            // queue order only matters for tracing
+        BucketMap bm; bm.n_agents = (uint32_t)G.N; bm.n_prev = c->n_queue_prev; bm.kind = 1;
+        if (!block_bucket_sort(qk, qa, nq, G.succ + (size_t)r * G.cap_succ, G.cap_succ, bm, sv, warp_sums))
+            block_sort_pairs(qk, qa, nq, G.cap_queue, sk, sv);
+    }
     __syncthreads();
     for (uint32_t i = tid; i < nq; i += blockDim.x) {
         int32_t a = qa[i];
@@ -396,6 +489,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
     }
     __syncthreads();
 
+    TS(2);   // queue drain
     if (ct && nq > 0) {
         // Depth-first contact tracing resolved in parallel.  Attempt key = (queue rank, level-0 slot, level-1 slot);
         // an attempt queues its candidate iff it is the smallest-key LIVE attempt on it that EXISTS; a level-1
@@ -492,11 +586,13 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
         __syncthreads();
     }
 
+    TS(3);   // contact tracing
     // vaccinate_people (main.pyx:560-583): top-down walk of the age-sorted range; eligibility only ever turns
     // off (dead / vaccinated / detected), so a per-programme cursor below which the walk resumes is exact.
     for (int p = 0; p < dp->n_vacc; p++) {
         int nr = dp->vacc_nr[p];
         if (!nr) continue;
+        if (tid == 0) c->any_vacc = 1u;
         int slot = dp->vacc_slot[p];
         int32_t s = G.age_start[dp->vacc_min_age[p]], en = G.age_start[dp->vacc_max_age[p] + 1];
         if (nr > en - s) nr = en - s;
@@ -526,10 +622,12 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
     }
     __syncthreads();
 
+    TS(4);   // vaccination
     if (tid == 0) {
         u32x4 x = philox(c->seed, 0u, (uint32_t)day, PU_START, 0);     // _iterate_people, main.pyx:1988
         c->start = x.x % (uint32_t)G.N;
         c->n_items = 0; c->n_succ = 0; c->n_events = 0;
+        c->n_queue_prev = nq;      // tomorrow's queue holds tracing keys whose rank field is < nq
         // dense days (> 1/24 of the agents infected) stream the packed words, sparse days walk the activity bitmap
         int infected = 0;
         for (int age = 0; age < G.n_ages; age++) infected += c->counts[RB_A_INFECTED][age];
@@ -959,9 +1057,11 @@ __global__ void __launch_bounds__(256) k_resolve(Eng G) {
     const uint32_t n = min(c->n_succ, G.cap_succ);
     const Attempt *succ = G.succ + (size_t)r * G.cap_succ;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Attempt at = succ[i];
-        if (G.winner[base + at.cand] != at.key) continue;     // first infector in sweep order wins
-        device_infect(G, r, c, (int32_t)at.cand, (int32_t)at.parent, G.hot[base + at.parent], 0, (int)(at.key & 127ull), false);
+        const Attempt at = succ[i];
+        const unsigned long long w = G.winner[base + at.cand];
+        const uint32_t src_h = G.hot[base + at.parent];       // in flight together with the conflict slot
+        if (w != at.key) continue;                             // first infector in sweep order wins
+        device_infect(G, r, c, (int32_t)at.cand, (int32_t)at.parent, src_h, 0, (int)(at.key & 127ull), false);
         G.winner[base + at.cand] = KEY_IDLE;
     }
 }
@@ -994,9 +1094,13 @@ __device__ void post_body(const Eng &G, const int r, SmemSmall &S) {
     unsigned long long *ek = G.ev_key + (size_t)r * G.cap_events;
     int32_t *ea = G.ev_agent + (size_t)r * G.cap_events;
     const int day = c->day;
+    if (G.dbg == 9 && threadIdx.x == 0) c->dbg_last = clock64();
     if (n > 0) {
-        block_sort_pairs(ek, ea, n, G.cap_events, sk, sv);
+        BucketMap bm; bm.n_agents = (uint32_t)G.N; bm.n_prev = 0; bm.kind = 0;
+        if (n > 1 && !block_bucket_sort(ek, ea, n, G.succ + (size_t)r * G.cap_succ, G.cap_succ, bm, sv, S.warp_sums))
+            block_sort_pairs(ek, ea, n, G.cap_events, sk, sv);
         __syncthreads();
+        TS(8);   // event sort
         const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
         const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
         MP fb; fb.a = 0; fb.b = NEG_INF; MP fi = fb;
@@ -1059,6 +1163,7 @@ __device__ void post_body(const Eng &G, const int r, SmemSmall &S) {
         if (tid == 0) { c->avail_beds = mp_apply(s_bed[blockDim.x - 1], beds0); c->avail_icu = mp_apply(s_icu[blockDim.x - 1], icu0); }
     }
     __syncthreads();
+    TS(9);   // capacity scan + outcomes
     if (tid == 0) {
         c->qsel ^= 1u;
         c->n_queue = min(c->n_newq, G.cap_queue);
@@ -1154,7 +1259,7 @@ struct rb_engine {
     int32_t day;
     float last_ms;
     int64_t launches;
-    int sweep_blocks, list_blocks;
+    int sweep_blocks, list_blocks, resolve_blocks;
     cudaGraphExec_t graph[2];
     bool have_graphs;
 };
@@ -1285,6 +1390,9 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     int per_rep = (sms * 8 + R - 1) / R; if (per_rep < 4) per_rep = 4;
     e->sweep_blocks = want < per_rep ? want : per_rep; if (e->sweep_blocks < 1) e->sweep_blocks = 1;
     e->list_blocks = (sms * 4 + R - 1) / R; if (e->list_blocks < 2) e->list_blocks = 2;
+    // k_resolve is a chain of dependent scattered accesses per infection: enough threads for one pass over the day's list
+    e->resolve_blocks = (int)((G.N / 128 + 255) / 256); if (e->resolve_blocks < e->list_blocks) e->resolve_blocks = e->list_blocks;
+    if (e->resolve_blocks > 64) e->resolve_blocks = 64;
     k_init<<<dim3(e->sweep_blocks, R), 256, 0, e->stream>>>(G); e->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
@@ -1364,7 +1472,7 @@ static void launch_segment(rb_engine *e, cudaStream_t st) {
     const Eng &G = e->G;
     k_sweep<<<dim3(e->sweep_blocks, G.R), SW_THREADS, 0, st>>>(G);
     k_expose<<<dim3(e->list_blocks, G.R), EX_THREADS, 0, st>>>(G);
-    k_resolve<<<dim3(e->list_blocks, G.R), 256, 0, st>>>(G);
+    k_resolve<<<dim3(e->resolve_blocks, G.R), 256, 0, st>>>(G);
     k_between<<<G.R, PRE_THREADS, 0, st>>>(G);
 }
 
@@ -1403,7 +1511,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     while (mid > 0) { CK(cudaGraphLaunch(e->graph[1], e->stream)); mid -= 1; e->launches += 4; }
     k_sweep<<<dim3(e->sweep_blocks, R), SW_THREADS, 0, e->stream>>>(G);
     k_expose<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G);
-    k_resolve<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G);
+    k_resolve<<<dim3(e->resolve_blocks, R), 256, 0, e->stream>>>(G);
     k_post<<<R, PRE_THREADS, 0, e->stream>>>(G);
     e->launches += 4;
     CK(cudaEventRecord(e->ev1, e->stream));
@@ -1425,7 +1533,7 @@ extern "C" int rb_step_profiled(rb_engine *e, int32_t n_days, float *ms_per_kern
         k_pre<<<R, PRE_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[1], e->stream));
         k_sweep<<<dim3(e->sweep_blocks, R), SW_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[2], e->stream));
         k_expose<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G); CK(cudaEventRecord(v[3], e->stream));
-        k_resolve<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G); CK(cudaEventRecord(v[4], e->stream));
+        k_resolve<<<dim3(e->resolve_blocks, R), 256, 0, e->stream>>>(G); CK(cudaEventRecord(v[4], e->stream));
         k_post<<<R, PRE_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[5], e->stream));
         e->launches += 5;
     }
@@ -1449,6 +1557,11 @@ extern "C" int rb_sync(rb_engine *e) {
 
 extern "C" int32_t rb_day(rb_engine *e) { return e->day; }
 extern "C" void rb_debug_flag(rb_engine *e, int32_t v) { e->G.dbg = v; }
+extern "C" int rb_debug_phase_cycles(rb_engine *e, int32_t replica, long long *out16) {
+    cudaSetDevice(e->cfg.device); cudaStreamSynchronize(e->stream);
+    RepCtr c; if (cudaMemcpy(&c, &e->G.ctr[replica], sizeof c, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    memcpy(out16, c.dbg_t, sizeof c.dbg_t); return 0;
+}
 extern "C" int32_t rb_row_len(rb_engine *e) { return e->G.row_len; }
 extern "C" float rb_last_step_ms(rb_engine *e) { return e->last_ms; }
 extern "C" int64_t rb_launch_count(rb_engine *e) { return e->launches; }
