@@ -165,7 +165,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--replicas', type=int, default=32, help='ensemble members (seeds) per GPU')
+    ap.add_argument('--replicas', type=int, default=128, help='ensemble members (seeds) per GPU')
     ap.add_argument('--days', type=int, default=180)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-cpu-baseline', action='store_true')
