@@ -99,18 +99,19 @@ def make_context(n_replicas, device, days, seed):
     return ctx
 
 
-def algorithmic_bytes(rows, n_agents, G):
+def algorithmic_bytes(s1, n_agents, n_replicas, G):
     """bytes_day = 4 N + 12 I_d + 8 E_d, summed over days and replicas.
-    rows: [R, D, row_len] stats rows (I_d = infected that day, E_d = contacts sampled that day)."""
+    s1: [D, row_len] sums over replicas of the stats rows (I_d = infected that day, E_d = contacts sampled that day)."""
     from reina_b200 import _abi
     nA = len(_abi.ATTRS)
     i_inf = _abi.ATTRS.index('infected')
-    I = rows[:, :, i_inf * G:(i_inf + 1) * G].sum(axis=2).astype(np.float64)          # state at start of day d
-    E = rows[:, :, nA * G + _abi.SCALARS.index('exposed_per_day')].astype(np.float64)  # contacts of day d-1
-    R, D = I.shape
-    sweep = 4.0 * n_agents * R * D + 12.0 * I.sum()
+    I = s1[:, i_inf * G:(i_inf + 1) * G].sum(axis=1)                     # state at start of day d, all replicas
+    E = s1[:, nA * G + _abi.SCALARS.index('exposed_per_day')]            # contacts of day d-1, all replicas
+    D = s1.shape[0]
+    sweep = 4.0 * n_agents * n_replicas * D + 12.0 * I.sum()
     total = sweep + 8.0 * E.sum()
-    return dict(sweep=sweep, total=total, mean_infected=float(I.mean()), mean_contacts=float(E[:, 1:].mean()) if D > 1 else 0.0)
+    return dict(sweep=sweep, total=total, mean_infected=float(I.mean() / n_replicas),
+                mean_contacts=float(E[1:].mean() / n_replicas) if D > 1 else 0.0)
 
 
 def cpu_baseline(days, seeds, processes):
@@ -206,16 +207,7 @@ def main():
     G = len(ctx.age_group_labels)
     seed_of = lambda step: 1_000_000 * (rank + 1) + 1000 * step     # fresh seeds every step, distinct per rank
 
-    def reduce_curves(rows):
-        """Final reduce of the daily curves: sum and sum of squares over all seeds of all GPUs (NCCL)."""
-        x = rows.astype(np.float64)
-        s1, s2 = x.sum(axis=0), (x * x).sum(axis=0)
-        if dist is not None:
-            import torch
-            t = torch.from_numpy(np.stack([s1, s2])).cuda()
-            dist.all_reduce(t)
-            s1, s2 = t[0].cpu().numpy(), t[1].cpu().numpy()
-        return s1, s2
+    from reina_b200 import ensemble
 
     # ---------------- device-resident arm (`value`) and end-to-end arm (`e2e`), same steps ----------------
     def one_step(step, timed):
@@ -224,11 +216,11 @@ def main():
         h2d = ctx.upload_inputs()                  # contact tables of every mobility epoch, from host memory
         ctx.run(D)                                 # schedule H2D + 180 simulated days + sync
         dev_ms = eng.last_step_ms()                # CUDA events around the 180-day run only
-        rows = ctx.series(0, D)                    # D2H of every daily series of every replica
-        s1, s2 = reduce_curves(rows)
+        s1, s2, n = ctx.moments(0, D)              # the step's result: sum / sum of squares of every daily series
+        s1g, s2g, ng = ensemble.reduce_moments(s1, s2, n)      # final reduce over the GPUs (NCCL all-reduce)
         wall = time.perf_counter() - t0
         h2d += D * 256                             # sizeof(rb_day_params) per day
-        return dev_ms, wall, rows, h2d, rows.nbytes
+        return dev_ms, wall, s1, h2d, s1.nbytes + s2.nbytes
 
     for step in range(a.warmup):
         one_step(step, False)
@@ -238,9 +230,9 @@ def main():
     launches0 = eng.launch_count()
     barrier()
     dev_ms_total, wall_total = 0.0, 0.0
-    rows = None
+    s1 = None
     for step in range(a.warmup, a.warmup + a.steps):
-        dev_ms, wall, rows, h2d, d2h = one_step(step, True)
+        dev_ms, wall, s1, h2d, d2h = one_step(step, True)
         dev_ms_total += dev_ms
         wall_total += wall
     barrier()
@@ -253,7 +245,7 @@ def main():
     ms_per_step = dev_ms_total / a.steps
     value = agent_days_step / (ms_per_step / 1e3)
     e2e_value = agent_days_step / (wall_total / a.steps)
-    alg = algorithmic_bytes(rows, N_AGENTS, G)
+    alg = algorithmic_bytes(s1, N_AGENTS, R, G)
 
     # ---------------- per-kernel device times (one extra run, events around every launch) ----------------
     ctx.reset(seed_of(a.warmup + a.steps - 1))

@@ -159,6 +159,11 @@ int32_t rb_row_len(rb_engine *e);   /* RB_N_ATTRS * n_groups + RB_N_SCALARS */
 /* out[replica][day][row_len], days [day0, day0+n) */
 int rb_read_stats(rb_engine *e, int32_t day0, int32_t n, int32_t *out);
 
+/* Ensemble moments of the stats rows, reduced on the device: for days [day0, day0+n) and every row column,
+ * sum[day][col] = sum over replicas of x and sumsq[day][col] = sum of x^2 (doubles, [n][row_len] each).  This is what a
+ * Monte-Carlo run returns (mean / std curves); it replaces the D2H copy of every replica's rows. */
+int rb_read_moments(rb_engine *e, int32_t day0, int32_t n, double *sum, double *sumsq);
+
 /* Context.get_population_stats(what) (main.pyx:1859-1866): per single-year age counter of one replica. */
 int rb_read_per_age(rb_engine *e, int32_t replica, int32_t attr, int32_t *out);
 

@@ -750,6 +750,18 @@ int ro_read_stats(rb_engine *e, int32_t day0, int32_t n, int32_t *out) {
                e->stats + ((size_t)ri * (e->cfg.max_days + 1) + day0) * e->row_len, sizeof(int32_t) * (size_t)n * e->row_len);
     return 0;
 }
+int ro_read_moments(rb_engine *e, int32_t day0, int32_t n, double *sum, double *sumsq) {
+    for (int d = 0; d < n; d++)
+        for (int col = 0; col < e->row_len; col++) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int ri = 0; ri < e->cfg.n_replicas; ri++) {
+                double v = (double)e->stats[((size_t)ri * (e->cfg.max_days + 1) + day0 + d) * e->row_len + col];
+                s1 += v; s2 += v * v;
+            }
+            sum[(size_t)d * e->row_len + col] = s1; sumsq[(size_t)d * e->row_len + col] = s2;
+        }
+    return 0;
+}
 int ro_read_per_age(rb_engine *e, int32_t replica, int32_t attr, int32_t *out) {
     memcpy(out, e->rep[replica].counts[attr], sizeof(int32_t) * e->cfg.n_ages); return 0;
 }

@@ -82,7 +82,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CUDA_LIB_PATH = os.path.join(_HERE, 'libreina_b200.so')
 
 SYMBOLS = ['create', 'destroy', 'reset', 'step_profiled', 'set_contact_table', 'set_schedule', 'step', 'sync', 'day',
-           'snapshot', 'row_len', 'read_stats', 'read_per_age', 'problem', 'sample', 'read_agents',
+           'snapshot', 'row_len', 'read_stats', 'read_moments', 'read_per_age', 'problem', 'sample', 'read_agents',
            'read_queue', 'read_available', 'last_step_ms', 'launch_count', 'last_error']
 
 
@@ -128,6 +128,7 @@ class Library:
         f['row_len'].argtypes = [vp]
         f['row_len'].restype = C.c_int32
         f['read_stats'].argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+        f['read_moments'].argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         f['read_per_age'].argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
         f['problem'].argtypes = [vp, C.POINTER(C.c_int32)]
         f['sample'].argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
@@ -227,6 +228,12 @@ class Engine:
         out = np.empty((self.n_replicas, n, self.row_len), dtype=np.int32)
         self.lib.check(self.lib.f['read_stats'](self.h, day0, n, _ptr(out, C.c_int32)), 'read_stats')
         return out
+
+    def read_moments(self, day0, n):
+        s1 = np.empty((n, self.row_len), dtype=np.float64)
+        s2 = np.empty((n, self.row_len), dtype=np.float64)
+        self.lib.check(self.lib.f['read_moments'](self.h, day0, n, _ptr(s1, C.c_double), _ptr(s2, C.c_double)), 'read_moments')
+        return s1, s2
 
     def read_per_age(self, replica, attr):
         out = np.empty(self.n_ages, dtype=np.int32)

@@ -71,11 +71,21 @@ struct DevTable {
     uint8_t place[RB_MAX_AGES][RB_MAX_ROWS];
     uint8_t lo_age[RB_MAX_AGES][RB_MAX_ROWS], hi_age[RB_MAX_AGES][RB_MAX_ROWS];
     uint8_t susc_uniform[RB_MAX_AGES][RB_MAX_ROWS];   // susceptibility identical for every age of the row's band
-    uint8_t guide[RB_MAX_AGES][256];                  // first row whose cum_p exceeds b/256: start of the row search
+    uint8_t guide[RB_MAX_AGES][1024];                 // first row whose cum_p exceeds b/1024: start of the row search
     uint8_t nguide[RB_MAX_AGES][2][64];               // first k with ncdf[k] > b/64: start of the contact-count search
 };
 
 struct Attempt { uint32_t cand, parent; unsigned long long key; };
+
+// Everything about one agent that only infections, tracing and capacity outcomes touch, in ONE 32-byte sector:
+// an infection then costs one random DRAM sector for the target and one for the infector instead of seven.
+struct __align__(32) AgentRec {
+    unsigned long long winner;       // atomicMin conflict slot, all-ones when idle
+    int32_t infector, first_child, next_sib;   // infection tree (replaces the malloc'd infectees[64], main.pyx:227-233)
+    uint32_t inf_key;                // (day << 8) | slot of this agent's infection: orders siblings
+    uint32_t cold;                   // other_people_infected 16b | ward_days 8b | icu_days 8b
+    int16_t vacc_day, pad;
+};
 
 struct RepCtr {
     int32_t counts[RB_N_ATTRS][RB_MAX_AGES];
@@ -101,10 +111,8 @@ struct Eng {
     int32_t dbg;                                   // measurement aid: 1/2/3 skip a sweep stage (timing experiments only)
     int32_t N, Npad, n_ages, n_groups, n_variants, R, max_days, row_len, n_import_classes, fhalf;
     uint32_t cap_items, cap_succ, cap_events, cap_queue;
-    uint32_t *hot, *cold, *inf_key;
-    int32_t *infector, *first_child, *next_sib;
-    int16_t *vacc_day;
-    unsigned long long *winner;
+    uint32_t *hot;
+    AgentRec *rec;
     uint32_t *sus;                                 // [R][sus_words] 1 bit per agent: still SUSCEPTIBLE (L2-resident gather target)
     int32_t sus_words;
     uint32_t *act;                                 // [R][sus_words] 1 bit per agent: has work in today's sweep (infected, or removed and not yet counted)
@@ -170,10 +178,10 @@ __device__ void device_infect(const Eng &G, int r, RepCtr *c, int32_t t, int32_t
     // the two atomics whose results are needed go first; the draws below hide their round trip
     uint32_t old = 0; int32_t prev_child = -1;
     if (src >= 0) {
-        old = atomicAdd(&G.cold[base + src], 1u);
-        prev_child = atomicExch(&G.first_child[base + src], t);
+        old = atomicAdd(&G.rec[base + src].cold, 1u);
+        prev_child = atomicExch(&G.rec[base + src].first_child, t);
     }
-    const int vd = c->any_vacc ? (int)G.vacc_day[base + t] : -1;     // nobody is vaccinated in most configurations
+    const int vd = c->any_vacc ? (int)G.rec[base + t].vacc_day : -1;     // nobody is vaccinated in most configurations
     const int age = age_of(G, t);
     const rb_variant *v0 = &G.variants[0];
     const bool vacc_eff = vd >= 0 && (day - vd) > 14;
@@ -182,10 +190,10 @@ __device__ void device_infect(const Eng &G, int r, RepCtr *c, int32_t t, int32_t
     const int dl = clamp255(round_to_int(gamma_f(c->seed, (uint32_t)t, (uint32_t)day, PU_INCUB, v0->incubation_kappa, v0->incubation_theta)));
     if (src >= 0) {
         variant = (int)H_VAR(src_h);
-        G.infector[base + t] = src;
+        G.rec[base + t].infector = src;
         if ((src_h & H_LIST) && (old & 0xffffu) >= MAX_INFECTEES) set_problem(c, RB_TOO_MANY_INFECTEES);
-        G.inf_key[base + t] = ((uint32_t)day << 8) | (uint32_t)slot;
-        G.next_sib[base + t] = prev_child;
+        G.rec[base + t].inf_key = ((uint32_t)day << 8) | (uint32_t)slot;
+        G.rec[base + t].next_sib = prev_child;
     }
     // a SUSCEPTIBLE agent's word carries nothing but the vaccinated flag, which vacc_day implies
     uint32_t nh = (vd >= 0 ? H_VACC : 0u) | RB_INCUBATION | ((uint32_t)sev << 3) | ((uint32_t)variant << 8) | ((uint32_t)dl << 14);
@@ -392,7 +400,7 @@ __device__ void import_infections(const Eng &G, int r, RepCtr *c, int count, int
 // its infectees in infection order (only while the tracer is infected and owns a list, :227-233, :305-307).
 __device__ int trace_candidates(const Eng &G, size_t base, int32_t x, uint32_t hx, int32_t *cand /*[65]*/, int *first_slot) {
     int n = 0;
-    int32_t inf = G.infector[base + x];
+    int32_t inf = G.rec[base + x].infector;
     *first_slot = 1;
     if (inf >= 0) { cand[0] = inf; n = 1; *first_slot = 0; }
     uint32_t st = H_STATE(hx);
@@ -400,8 +408,8 @@ __device__ int trace_candidates(const Eng &G, size_t base, int32_t x, uint32_t h
         uint32_t keys[MAX_INFECTEES];
         int m = 0;
         int32_t *kids = cand + 1;
-        for (int32_t ch = G.first_child[base + x]; ch >= 0 && m < MAX_INFECTEES; ch = G.next_sib[base + ch]) {
-            uint32_t k = G.inf_key[base + ch];
+        for (int32_t ch = G.rec[base + x].first_child; ch >= 0 && m < MAX_INFECTEES; ch = G.rec[base + ch].next_sib) {
+            uint32_t k = G.rec[base + ch].inf_key;
             int j = m++;
             while (j > 0 && keys[j - 1] > k) { keys[j] = keys[j - 1]; kids[j] = kids[j - 1]; j--; }
             keys[j] = k; kids[j] = ch;
@@ -494,7 +502,6 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
         // Depth-first contact tracing resolved in parallel.  Attempt key = (queue rank, level-0 slot, level-1 slot);
         // an attempt queues its candidate iff it is the smallest-key LIVE attempt on it that EXISTS; a level-1
         // attempt exists iff its tracer was itself queued by a level-0 attempt (main.pyx:498-499, 505-512).
-        unsigned long long *win = G.winner + base;
         Attempt *l0 = G.succ + (size_t)r * G.cap_succ;
         Attempt *l1 = (Attempt *)(G.items + (size_t)r * G.cap_items);
         const uint32_t cap_l1 = G.cap_items / 2;
@@ -510,7 +517,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
                 if (!chance(u01d(rx.x, rx.y), ptr)) continue;
                 unsigned long long key = ((unsigned long long)i << 14) | ((unsigned long long)a << 7);
                 uint32_t idx = atomicAdd(&c->n_l0, 1u);
-                if (idx < G.cap_succ) { l0[idx].cand = (uint32_t)cc; l0[idx].parent = (uint32_t)x; l0[idx].key = key; atomicMin(&win[cc], key); }
+                if (idx < G.cap_succ) { l0[idx].cand = (uint32_t)cc; l0[idx].parent = (uint32_t)x; l0[idx].key = key; atomicMin(&G.rec[base + (cc)].winner, key); }
                 else set_problem(c, RB_OTHER_FAILURE);
             }
         }
@@ -518,7 +525,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
         uint32_t n0 = min(c->n_l0, G.cap_succ);
         for (uint32_t j = tid; j < n0; j += blockDim.x) {
             Attempt at = l0[j];
-            if (win[at.cand] != at.key) continue;
+            if (G.rec[base + (at.cand)].winner != at.key) continue;
             int32_t x = (int32_t)at.cand;
             int32_t cand[MAX_INFECTEES + 1]; int first;
             int n = trace_candidates(G, base, x, G.hot[base + x], cand, &first);
@@ -539,7 +546,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
         uint32_t *edst = (uint32_t *)(G.ev_agent + (size_t)r * G.cap_events);
         const uint32_t cap_e = G.cap_events;
         for (uint32_t k = tid; k < n1; k += blockDim.x) {
-            unsigned long long w = win[l1[k].cand];
+            unsigned long long w = G.rec[base + (l1[k].cand)].winner;
             if (w != KEY_IDLE && l1[k].key < w) {
                 uint32_t idx = atomicAdd(&c->n_edges, 1u);
                 if (idx < cap_e) { esrc[idx] = l1[k].parent; edst[idx] = l1[k].cand; } else set_problem(c, RB_OTHER_FAILURE);
@@ -553,36 +560,36 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
             for (;;) {
                 unsigned long long best = KEY_IDLE; uint32_t bd = 0;
                 for (uint32_t k = 0; k < ne; k++) {
-                    unsigned long long w = win[edst[k]];
+                    unsigned long long w = G.rec[base + (edst[k])].winner;
                     if (!(w & CT_DECIDED) && (w & CT_KEYMASK) < best) { best = w & CT_KEYMASK; bd = edst[k]; }
                 }
                 if (best == KEY_IDLE) break;
                 bool dead = false;
-                for (uint32_t k = 0; k < ne; k++) if (edst[k] == bd && !(win[esrc[k]] & CT_DEAD)) { dead = true; break; }
-                win[bd] = best | CT_DECIDED | (dead ? CT_DEAD : 0ull);
+                for (uint32_t k = 0; k < ne; k++) if (edst[k] == bd && !(G.rec[base + (esrc[k])].winner & CT_DEAD)) { dead = true; break; }
+                G.rec[base + (bd)].winner = best | CT_DECIDED | (dead ? CT_DEAD : 0ull);
             }
             for (uint32_t k = 0; k < ne; k++) {
-                unsigned long long w = win[edst[k]];
+                unsigned long long w = G.rec[base + (edst[k])].winner;
                 if (w == KEY_IDLE) continue;
-                win[edst[k]] = (w & CT_DEAD) ? KEY_IDLE : (w & CT_KEYMASK);
+                G.rec[base + (edst[k])].winner = (w & CT_DEAD) ? KEY_IDLE : (w & CT_KEYMASK);
             }
         }
         __syncthreads();
         for (uint32_t k = tid; k < n1; k += blockDim.x) {
             Attempt e = l1[k];
-            if (win[e.parent] == (e.key & ~127ull)) atomicMin(&win[e.cand], e.key);
+            if (G.rec[base + (e.parent)].winner == (e.key & ~127ull)) atomicMin(&G.rec[base + (e.cand)].winner, e.key);
         }
         __syncthreads();
         for (uint32_t j = tid; j < n0 + n1; j += blockDim.x) {
             Attempt e = j < n0 ? l0[j] : l1[j - n0];
-            if (win[e.cand] != e.key) continue;
-            if (j >= n0 && win[e.parent] != (e.key & ~127ull)) continue;
+            if (G.rec[base + (e.cand)].winner != e.key) continue;
+            if (j >= n0 && G.rec[base + (e.parent)].winner != (e.key & ~127ull)) continue;
             uint32_t idx = atomicAdd(&c->n_newq, 1u);
             if (idx < G.cap_queue) { nk[idx] = e.key; na[idx] = (int32_t)e.cand; } else set_problem(c, RB_OTHER_FAILURE);
             G.hot[base + e.cand] |= H_QUEUED;
         }
         __syncthreads();
-        for (uint32_t j = tid; j < n0 + n1; j += blockDim.x) { Attempt e = j < n0 ? l0[j] : l1[j - n0]; win[e.cand] = KEY_IDLE; }
+        for (uint32_t j = tid; j < n0 + n1; j += blockDim.x) { Attempt e = j < n0 ? l0[j] : l1[j - n0]; G.rec[base + (e.cand)].winner = KEY_IDLE; }
         __syncthreads();
     }
 
@@ -609,7 +616,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
             int want = nr - done;
             if (el && rank <= want) {
                 G.hot[base + idx] = h | H_VACC;
-                G.vacc_day[base + idx] = (int16_t)day;
+                G.rec[base + idx].vacc_day = (int16_t)day;
                 count_add(c, RB_A_VACCINATED, age_of(G, idx), 1);
                 if (rank == want) sh_i[1] = idx - 1;      // walk stops right below the last person vaccinated
             }
@@ -749,7 +756,7 @@ __device__ __forceinline__ void stage_transition(const Eng &G, int r, RepCtr *c,
             u = ((1.0f - v->ratio_in_ward) - v->ratio_before_hospitalisation) * T;
         }
         const uint32_t wd = (uint32_t)clamp255(round_to_int(w)), ud = (uint32_t)clamp255(round_to_int(u));
-        if (wd | ud) atomicOr(&G.cold[base + a], (wd << 16) | (ud << 24));
+        if (wd | ud) atomicOr(&G.rec[base + a].cold, (wd << 16) | (ud << 24));
         h = H_SET_DL(H_SET_STATE(h, RB_ILLNESS), dl);
         if (sev != RB_ASYMPTOMATIC && !(h & H_DET)) {
             // seek_testing, main.pyx:595-615
@@ -812,7 +819,7 @@ __device__ __forceinline__ void stage_active(const Eng &G, int r, RepCtr *c, War
         const uint32_t st = H_STATE(h);
         if (st >= RB_RECOVERED) {          // R bookkeeping, main.pyx:1969-1972 (only agents not yet included reach here)
             atomicAdd(&c->total_infectors, 1);
-            atomicAdd(&c->total_infections, (int)(G.cold[base + a] & 0xffffu));
+            atomicAdd(&c->total_infections, (int)(G.rec[base + a].cold & 0xffffu));
             G.hot[base + a] = h | H_INCL;
             atomicAnd(&G.act[(size_t)r * G.sus_words + (a >> 5)], ~(1u << (a & 31)));   // nothing left to do for this agent
         } else if (h & H_FRESH) {          // infected today before the sweep: wait until tomorrow, main.pyx:402-403
@@ -971,7 +978,7 @@ __device__ __forceinline__ void expose_survivors(const Eng &G, int r, RepCtr *c,
     }
     const unsigned long long key = ((unsigned long long)sweep_pos(G, c, a) << 7) | slot;
     const uint32_t idx = atomicAdd(&c->n_succ, 1u);
-    if (idx < G.cap_succ) { succ[idx].cand = t; succ[idx].parent = a; succ[idx].key = key; atomicMin(&G.winner[base + t], key); }
+    if (idx < G.cap_succ) { succ[idx].cand = t; succ[idx].parent = a; succ[idx].key = key; atomicMin(&G.rec[base + t].winner, key); }
     else set_problem(c, RB_OTHER_FAILURE);
 }
 
@@ -1020,8 +1027,8 @@ __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
             if (w < ncnt) {
                 const uint32_t word = words[w];
                 const double u = (double)(word >> 8) * (1.0 / 16777216.0);
-                // linear scan for the first row with u < cum_p; rows below guide[u's top byte] cannot match
-                row = tb->guide[age][word >> 24];
+                // linear scan for the first row with u < cum_p; rows below guide[u's top 10 bits] cannot match
+                row = tb->guide[age][word >> 22];
                 while ((int)row < nrows - 1 && !(u < cum[row])) row++;   // last row on overrun: the reference fails there (p ~ 1e-15)
                 places += 1u << (5 * tb->place[age][row]);               // daily_contacts[place]++ (main.pyx:1571)
                 pass = (int)(word & 255u) < kq;
@@ -1058,11 +1065,11 @@ __global__ void __launch_bounds__(256) k_resolve(Eng G) {
     const Attempt *succ = G.succ + (size_t)r * G.cap_succ;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Attempt at = succ[i];
-        const unsigned long long w = G.winner[base + at.cand];
+        const unsigned long long w = G.rec[base + at.cand].winner;
         const uint32_t src_h = G.hot[base + at.parent];       // in flight together with the conflict slot
         if (w != at.key) continue;                             // first infector in sweep order wins
         device_infect(G, r, c, (int32_t)at.cand, (int32_t)at.parent, src_h, 0, (int)(at.key & 127ull), false);
-        G.winner[base + at.cand] = KEY_IDLE;
+        G.rec[base + at.cand].winner = KEY_IDLE;
     }
 }
 
@@ -1125,7 +1132,7 @@ __device__ void post_body(const Eng &G, const int r, SmemSmall &S) {
                 const uint32_t sev = H_SEV(h);
                 const rb_variant *v = &G.variants[H_VAR(h)];
                 const int age = age_of(G, a);
-                const uint32_t cold = G.cold[base + a];
+                const uint32_t cold = G.rec[base + a].cold;
                 const bool ok = type == EV_HOSP_CLAIM ? beds > 0 : icu > 0;
                 bool dies = false;
                 if (!ok) {      // Disease.dies_in_hospital(care_available=False), main.pyx:957-974
@@ -1189,9 +1196,8 @@ __global__ void k_init(Eng G) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < G.Npad; i += gridDim.x * blockDim.x) {
         // padding words beyond N are marked RECOVERED+included so that the sweep skips them
         G.hot[base + i] = i < G.N ? 0u : (RB_RECOVERED | H_INCL);
-        G.cold[base + i] = 0; G.inf_key[base + i] = 0;
-        G.infector[base + i] = -1; G.first_child[base + i] = -1; G.next_sib[base + i] = -1;
-        G.vacc_day[base + i] = -1; G.winner[base + i] = KEY_IDLE;
+        AgentRec z; z.winner = KEY_IDLE; z.infector = -1; z.first_child = -1; z.next_sib = -1; z.inf_key = 0; z.cold = 0; z.vacc_day = -1; z.pad = 0;
+        G.rec[base + i] = z;
     }
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < G.sus_words; w += gridDim.x * blockDim.x) {
         int first = w * 32;
@@ -1204,6 +1210,19 @@ __global__ void k_init(Eng G) {
 __global__ void k_snapshot(Eng G) {
     __shared__ int32_t srow[RB_N_ATTRS * 16 + RB_N_SCALARS];
     write_stats_row(G, blockIdx.x, &G.ctr[blockIdx.x], srow);
+}
+
+// Per-day metric aggregation across the ensemble: sum and sum of squares over replicas of every stats column.
+__global__ void k_moments(Eng G, int day0, double *out_sum, double *out_sq) {
+    const int d = blockIdx.x;
+    for (int col = threadIdx.x; col < G.row_len; col += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int r = 0; r < G.R; r++) {
+            const double v = (double)G.stats[((size_t)r * (G.max_days + 1) + day0 + d) * G.row_len + col];
+            s1 += v; s2 += v * v;
+        }
+        out_sum[(size_t)d * G.row_len + col] = s1; out_sq[(size_t)d * G.row_len + col] = s2;
+    }
 }
 
 // Context.sample, main.pyx:2047-2101
@@ -1343,8 +1362,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     G.cap_queue = pow2_at_least((uint64_t)N / 8 + 2048);
     const size_t RN = (size_t)R * G.Npad;
     G.sus_words = ((G.Npad + 31) / 32 + 32 + 3) & ~3;     // multiple of 4 words: the sweep reads the bitmaps 16 bytes at a time
-    if (dalloc(e, &G.hot, RN) || dalloc(e, &G.cold, RN) || dalloc(e, &G.inf_key, RN) || dalloc(e, &G.infector, RN) ||
-        dalloc(e, &G.first_child, RN) || dalloc(e, &G.next_sib, RN) || dalloc(e, &G.vacc_day, RN) || dalloc(e, &G.winner, RN) ||
+    if (dalloc(e, &G.hot, RN) || dalloc(e, &G.rec, RN) ||
         dalloc(e, &G.sus, (size_t)R * G.sus_words) || dalloc(e, &G.act, (size_t)R * G.sus_words) || dalloc(e, &G.items, (size_t)R * G.cap_items) || dalloc(e, &G.succ, (size_t)R * G.cap_succ) ||
         dalloc(e, &G.ev_key, (size_t)R * G.cap_events) || dalloc(e, &G.ev_agent, (size_t)R * G.cap_events) ||
         dalloc(e, &G.q_key, (size_t)R * 2 * G.cap_queue) || dalloc(e, &G.q_agent, (size_t)R * 2 * G.cap_queue) ||
@@ -1439,15 +1457,14 @@ extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *
     }
     for (int age = 0; age < e->cfg.n_ages; age++)
         for (int cls = 0; cls < 2; cls++)
-            for (int b = 0; b < 64; b++) {
-                int limit = cls ? 5 : 100, k = 0;
+            for (int b = 0, k = 0; b < 64; b++) {
+                const int limit = cls ? 5 : 100;
                 while (k < limit && !(h->ncdf[age][cls][k] > (double)b / 64.0)) k++;
                 h->nguide[age][cls][b] = (uint8_t)k;
             }
     for (int age = 0; age < e->cfg.n_ages; age++)
-        for (int b = 0; b < 256; b++) {
-            int i = 0;
-            while (i < n_rows[age] - 1 && !(h->cum_p[age][i] > (double)b / 256.0)) i++;
+        for (int b = 0, i = 0; b < 1024; b++) {          // cum_p is non-decreasing: the start row only moves forward
+            while (i < n_rows[age] - 1 && !(h->cum_p[age][i] > (double)b / 1024.0)) i++;
             h->guide[age][b] = (uint8_t)i;
         }
     DevTable *d = e->tables[epoch];
@@ -1584,6 +1601,20 @@ extern "C" int rb_read_stats(rb_engine *e, int32_t day0, int32_t n, int32_t *out
     return 0;
 }
 
+extern "C" int rb_read_moments(rb_engine *e, int32_t day0, int32_t n, double *sum, double *sumsq) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (day0 < 0 || n < 1 || day0 + n > e->cfg.max_days + 1) { snprintf(g_err, sizeof g_err, "stats range"); return 1; }
+    const size_t cnt = (size_t)n * e->G.row_len;
+    double *d; CK(cudaMalloc(&d, sizeof(double) * 2 * cnt));
+    k_moments<<<n, 160, 0, e->stream>>>(e->G, day0, d, d + cnt); e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(sum, d, sizeof(double) * cnt, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(sumsq, d + cnt, sizeof(double) * cnt, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d);
+    return 0;
+}
+
 extern "C" int rb_read_per_age(rb_engine *e, int32_t replica, int32_t attr, int32_t *out) {
     CK(cudaSetDevice(e->cfg.device));
     if (replica < 0 || replica >= e->G.R || attr < 0 || attr >= RB_N_ATTRS) { snprintf(g_err, sizeof g_err, "bad replica/attr"); return 1; }
@@ -1620,9 +1651,11 @@ extern "C" int rb_read_agents(rb_engine *e, int32_t replica, rb_agent *out) {
     const int N = G.N; const size_t base = (size_t)replica * G.Npad;
     std::vector<uint32_t> hot(N), cold(N); std::vector<int32_t> inf(N); std::vector<int16_t> vd(N);
     CK(cudaMemcpy(hot.data(), G.hot + base, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(cold.data(), G.cold + base, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(inf.data(), G.infector + base, sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(vd.data(), G.vacc_day + base, sizeof(int16_t) * N, cudaMemcpyDeviceToHost));
+    {
+        std::vector<AgentRec> rec(N);
+        CK(cudaMemcpy(rec.data(), G.rec + base, sizeof(AgentRec) * N, cudaMemcpyDeviceToHost));
+        for (int a = 0; a < N; a++) { cold[a] = rec[a].cold; inf[a] = rec[a].infector; vd[a] = rec[a].vacc_day; }
+    }
     for (int a = 0; a < N; a++) {
         uint32_t h = hot[a]; rb_agent *o = &out[a];
         o->infector = inf[a]; o->n_infected = (int32_t)(cold[a] & 0xffffu);

@@ -56,7 +56,6 @@ def run_ensemble(make_context, days, replicas_per_rank, seed0=0, rank=0):
     make_context(n_replicas, random_seed) -> reina_b200.model.Context with interventions added."""
     ctx = make_context(replicas_per_rank, seeds_for_rank(seed0, replicas_per_rank, rank))
     ctx.run(days)
-    rows = ctx.series(0, days)
-    s1, s2, n = reduce_moments(*curve_moments(rows))
+    s1, s2, n = reduce_moments(*ctx.moments(0, days))      # reduced over replicas on the device, over ranks by NCCL/gloo
     mean, std = mean_std(s1, s2, n)
-    return dict(mean=mean, std=std, n=n, local_rows=rows, names=ctx.row_layout())
+    return dict(mean=mean, std=std, n=n, names=ctx.row_layout())

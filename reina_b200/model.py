@@ -444,6 +444,12 @@ class Context:
         self._engine.sync()
         return self._engine.read_stats(day0, days)
 
+    def moments(self, day0=0, days=None):
+        """Ensemble moments reduced on the device: (sum, sum of squares, n_replicas) of every stats column per day."""
+        days = self.day - day0 if days is None else days
+        s1, s2 = self._engine.read_moments(day0, days)
+        return s1, s2, self.n_replicas
+
     def row_layout(self):
         G = len(self.age_group_labels)
         names = ['%s[%s]' % (a, g) for a in ATTRS for g in self.age_group_labels]
