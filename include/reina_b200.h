@@ -184,6 +184,23 @@ float rb_last_step_ms(rb_engine *e);
  * (ms_per_kernel[RB_N_KERNELS], order: pre, sweep, expose, resolve, post).  Measurement aid for bench.py. */
 #define RB_N_KERNELS 5
 int rb_step_profiled(rb_engine *e, int32_t n_days, float *ms_per_kernel);
+/* ---- Population-sharded mode (BASELINE configs[4]; no reference counterpart: the reference is one process).
+ * One process per GPU; every rank creates the same engine (same inputs, seed, schedule, n_replicas = 1) and then joins:
+ * rank 0 obtains a 128-byte NCCL unique id with rb_shard_unique_id and hands it to the others by any means; each rank
+ * calls rb_shard_init(e, rank, nranks, id, exchange_capacity) before the first rb_step.  Agents are dealt to the ranks in
+ * stripes of 4096 (age-sorted order, so every rank holds ~1/nranks of every age).  A rank sweeps and samples contacts only
+ * for the agents it owns; once per simulated day the ranks all-gather (NCCL) their day's cross-shard events -- successful
+ * transmissions, state changes, test-queue entries, capacity events, counter deltas -- and every rank applies all of them,
+ * so counters, queues and every rb_read_* result are identical on all ranks and bit-identical to a single-GPU run.
+ * Per-agent day counters and severity are authoritative on the owning rank only (rb_read_agents: take agent a from rank
+ * (a >> 12) % nranks).  exchange_capacity scales the per-day message capacity (0 = default); overflow sets RB_OTHER_FAILURE.
+ * libnccl.so.2 is loaded at run time by these calls only. */
+int rb_shard_unique_id(uint8_t *out128);
+int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const uint8_t *unique_id128, float exchange_capacity);
+int32_t rb_shard_rank(rb_engine *e);
+int32_t rb_shard_nranks(rb_engine *e);
+int64_t rb_shard_message_bytes(rb_engine *e);   /* bytes each rank contributes to the daily all-gather */
+
 /* number of kernel launches issued by this handle so far */
 int64_t rb_launch_count(rb_engine *e);
 const char *rb_last_error(void);

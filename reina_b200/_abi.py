@@ -86,6 +86,16 @@ SYMBOLS = ['create', 'destroy', 'reset', 'step_profiled', 'set_contact_table', '
            'read_queue', 'read_available', 'last_step_ms', 'launch_count', 'last_error']
 
 
+# population-sharded mode: exported by the CUDA library only (the sequential CPU oracle has no ranks)
+SHARD_SYMBOLS = ['shard_unique_id', 'shard_init', 'shard_rank', 'shard_nranks', 'shard_message_bytes']
+SH_SHIFT = 12      # ownership stripes of 4096 agents, dealt round-robin over the ranks (engine.cu owns())
+
+
+def owner_of(agent_index, nranks):
+    """Rank that owns (sweeps) each agent in population-sharded mode."""
+    return (np.asarray(agent_index) >> SH_SHIFT) % nranks
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -141,6 +151,15 @@ class Library:
         f['launch_count'].restype = C.c_int64
         f['last_error'].argtypes = []
         f['last_error'].restype = C.c_char_p
+        if prefix == 'rb_':
+            for name in SHARD_SYMBOLS:
+                f[name] = getattr(self.dll, prefix + name)
+            f['shard_unique_id'].argtypes = [C.c_char_p]
+            f['shard_init'].argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_float]
+            f['shard_rank'].argtypes = [vp]
+            f['shard_nranks'].argtypes = [vp]
+            f['shard_message_bytes'].argtypes = [vp]
+            f['shard_message_bytes'].restype = C.c_int64
         self.f = f
 
     def check(self, rc, what):
@@ -179,7 +198,14 @@ class Engine:
                                   varr, _ptr(import_lo, C.c_int32), _ptr(import_hi, C.c_int32),
                                   _ptr(import_cum, C.c_float), C.byref(h)), 'create')
         self.h = h
+        self.rank, self.nranks = 0, 1
         self.row_len = lib.f['row_len'](h)
+
+    def shard_init(self, rank, nranks, unique_id, exchange_capacity=0.0):
+        """Join `nranks` engines (one per GPU / process) into one population-sharded simulation."""
+        assert len(unique_id) == 128
+        self.lib.check(self.lib.f['shard_init'](self.h, rank, nranks, bytes(unique_id), exchange_capacity), 'shard_init')
+        self.rank, self.nranks = rank, nranks
 
     def close(self):
         if getattr(self, 'h', None):
@@ -272,3 +298,11 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.f['launch_count'](self.h))
+
+
+def shard_unique_id(lib=None):
+    """A fresh NCCL unique id (128 bytes): rank 0 creates it and hands it to the other ranks."""
+    lib = lib or cuda_library()
+    buf = C.create_string_buffer(128)
+    lib.check(lib.f['shard_unique_id'](buf), 'shard_unique_id')
+    return buf.raw

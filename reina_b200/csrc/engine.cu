@@ -24,6 +24,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <dlfcn.h>
+#include <nccl.h>      // types only: libnccl is loaded at run time by rb_shard_init, single-GPU use never needs it
+
 #include <vector>
 
 #include "../../include/reina_b200.h"
@@ -102,7 +105,9 @@ struct RepCtr {
     uint32_t any_vacc;                            // set once the first vaccination programme starts
     uint32_t n_l0, n_l1, n_edges, stream_mode;   // stream_mode: today's sweep streams the packed words instead of the activity bitmap
     int32_t vacc_cursor[RB_MAX_VACC];
-    int32_t pad[6];
+    uint32_t n_upd;                               // population-sharded mode: packed-word updates logged by today's sweep
+    uint32_t n_q_base;                            // entries contact tracing put into tomorrow's queue before the sweep
+    int32_t pad[4];
     long long dbg_t[16];                          // measurement aid: cycles spent per phase of the day-boundary kernel
     long long dbg_last;
 };
@@ -129,7 +134,41 @@ struct Eng {
     const uint8_t *age_blk;                        // age of agent (b << 10): coarse index into age_start
     const int32_t *group_of_age;
     const int32_t *import_lo, *import_hi; const float *import_cum;
+    // population-sharded mode (rb_shard_init): every rank holds the whole state, sweeps and exposes only the agents
+    // it owns, and publishes what the others must know in its slot of the exchange buffer (one all-gather per day)
+    int32_t rank, nranks;
+    uint8_t *xbuf; size_t xslot;                   // [nranks] message slots; slot `rank` is written locally
+    uint32_t xcap_q, xcap_ev, xcap_upd, xcap_succ;
 };
+
+// Ownership: stripes of 4096 agents (one warp step of the sweep) dealt round-robin, so every rank holds ~1/nranks of every age.
+#define SH_SHIFT 12
+__device__ __forceinline__ bool owns(const Eng &G, uint32_t a) { return G.nranks == 1 || (int)((a >> SH_SHIFT) % (uint32_t)G.nranks) == G.rank; }
+
+// One rank's message: a RepCtr used as the header (count deltas of the sweep, list lengths) followed by the lists.
+struct XSlot {
+    RepCtr *hdr;
+    unsigned long long *q_key; int32_t *q_agent;     // test-queue entries created by the sweep
+    unsigned long long *ev_key; int32_t *ev_agent;   // capacity events
+    uint2 *upd;                                      // (agent, packed word) after a state change
+    struct Attempt *succ;                            // successful transmissions
+};
+__host__ __device__ inline size_t xalign(size_t x) { return (x + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t xslot_bytes(uint32_t cq, uint32_t ce, uint32_t cu, uint32_t cs) {
+    return xalign(sizeof(RepCtr)) + xalign(8ull * cq) + xalign(4ull * cq) + xalign(8ull * ce) + xalign(4ull * ce) + xalign(8ull * cu) + xalign(16ull * cs);
+}
+__device__ __forceinline__ XSlot xslot_of(const Eng &G, int rk) {
+    uint8_t *p = G.xbuf + (size_t)rk * G.xslot;
+    XSlot s;
+    s.hdr = (RepCtr *)p; p += xalign(sizeof(RepCtr));
+    s.q_key = (unsigned long long *)p; p += xalign(8ull * G.xcap_q);
+    s.q_agent = (int32_t *)p; p += xalign(4ull * G.xcap_q);
+    s.ev_key = (unsigned long long *)p; p += xalign(8ull * G.xcap_ev);
+    s.ev_agent = (int32_t *)p; p += xalign(4ull * G.xcap_ev);
+    s.upd = (uint2 *)p; p += xalign(8ull * G.xcap_upd);
+    s.succ = (struct Attempt *)p;
+    return s;
+}
 
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ int age_of(const Eng &G, int32_t a) {
@@ -185,9 +224,12 @@ __device__ void device_infect(const Eng &G, int r, RepCtr *c, int32_t t, int32_t
     const int age = age_of(G, t);
     const rb_variant *v0 = &G.variants[0];
     const bool vacc_eff = vd >= 0 && (day - vd) > 14;
-    u32x4 x = philox(c->seed, (uint32_t)t, (uint32_t)day, PU_SEVERITY, 0);
-    const int sev = symptom_severity(v0, age, u01f(x.x), vacc_eff);
-    const int dl = clamp255(round_to_int(gamma_f(c->seed, (uint32_t)t, (uint32_t)day, PU_INCUB, v0->incubation_kappa, v0->incubation_theta)));
+    int sev = 0, dl = 0;
+    if (owns(G, (uint32_t)t)) {     // severity and day counters are only ever read by the owner's sweep (sharded mode)
+        u32x4 x = philox(c->seed, (uint32_t)t, (uint32_t)day, PU_SEVERITY, 0);
+        sev = symptom_severity(v0, age, u01f(x.x), vacc_eff);
+        dl = clamp255(round_to_int(gamma_f(c->seed, (uint32_t)t, (uint32_t)day, PU_INCUB, v0->incubation_kappa, v0->incubation_theta)));
+    }
     if (src >= 0) {
         variant = (int)H_VAR(src_h);
         G.rec[base + t].infector = src;
@@ -639,6 +681,11 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
         int infected = 0;
         for (int age = 0; age < G.n_ages; age++) infected += c->counts[RB_A_INFECTED][age];
         c->stream_mode = (long long)infected * 24 > (long long)G.N ? 1u : 0u;
+        c->n_q_base = c->n_newq;
+    }
+    if (G.xbuf) {     // this rank's message header: the sweep and the contact kernel add to it from zero
+        uint32_t *hw = (uint32_t *)xslot_of(G, G.rank).hdr;
+        for (int i = tid; i < (int)(sizeof(RepCtr) / 4); i += blockDim.x) hw[i] = 0u;
     }
 }
 
@@ -673,8 +720,31 @@ __device__ __forceinline__ uint32_t ring_push(uint32_t *ra, uint32_t *rb, uint32
     return tail + __popc(m);
 }
 
+// Where the sweep puts what other kernels (and, in population-sharded mode, other ranks) consume.  Single GPU: the
+// replica's own counters and lists.  Sharded: this rank's message slot, merged on every rank by k_merge.
+struct SweepOut {
+    RepCtr *cd;                                        // counters the sweep ADDS to
+    unsigned long long *q_key; int32_t *q_agent; uint32_t cap_q;
+    unsigned long long *ev_key; int32_t *ev_agent; uint32_t cap_ev;
+    uint2 *upd; uint32_t cap_upd;                      // null on a single GPU
+};
+__device__ __forceinline__ SweepOut sweep_out(const Eng &G, int r, RepCtr *c) {
+    SweepOut O;
+    if (!G.xbuf) {
+        const size_t qb = ((size_t)r * 2 + (c->qsel ^ 1u)) * G.cap_queue;
+        O.cd = c; O.q_key = G.q_key + qb; O.q_agent = G.q_agent + qb; O.cap_q = G.cap_queue;
+        O.ev_key = G.ev_key + (size_t)r * G.cap_events; O.ev_agent = G.ev_agent + (size_t)r * G.cap_events; O.cap_ev = G.cap_events;
+        O.upd = nullptr; O.cap_upd = 0;
+    } else {
+        const XSlot x = xslot_of(G, G.rank);
+        O.cd = x.hdr; O.q_key = x.q_key; O.q_agent = x.q_agent; O.cap_q = G.xcap_q;
+        O.ev_key = x.ev_key; O.ev_agent = x.ev_agent; O.cap_ev = G.xcap_ev; O.upd = x.upd; O.cap_upd = G.xcap_upd;
+    }
+    return O;
+}
+
 // stage E: get_exposed_people / get_nr_contacts (main.pyx:936-955, 1308-1320) + work-item emission
-__device__ __forceinline__ void stage_expose(const Eng &G, RepCtr *c, const DevTable *tb, const WarpRings &W, uint32_t head, uint32_t m,
+__device__ __forceinline__ void stage_expose(const Eng &G, RepCtr *c, RepCtr *cd, const DevTable *tb, const WarpRings &W, uint32_t head, uint32_t m,
                                              uint2 *items, int lane) {
     uint32_t cnt = 0, ncont = 0, desc = 0, a = 0;
     if ((uint32_t)lane < m) {
@@ -703,9 +773,9 @@ __device__ __forceinline__ void stage_expose(const Eng &G, RepCtr *c, const DevT
     uint32_t ctot = ncont;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ctot += __shfl_xor_sync(0xffffffffu, ctot, o);
-    if (lane == 31) { gbase = atomicAdd(&c->n_items, wtot); atomicAdd(&c->exposed_per_day, (int)ctot); }
+    if (lane == 31) { gbase = atomicAdd(&c->n_items, wtot); atomicAdd(&cd->exposed_per_day, (int)ctot); }
     gbase = __shfl_sync(0xffffffffu, gbase, 31);
-    if (gbase + wtot > G.cap_items) { if (lane == 0) set_problem(c, RB_OTHER_FAILURE); return; }
+    if (gbase + wtot > G.cap_items) { if (lane == 0) set_problem(cd, RB_OTHER_FAILURE); return; }
     for (uint32_t t0 = 0; t0 < wtot; t0 += 32) {
         const uint32_t t = t0 + lane;
         int lo = 0;     // owner = largest lane whose exclusive prefix is <= t
@@ -723,17 +793,18 @@ __device__ __forceinline__ void stage_expose(const Eng &G, RepCtr *c, const DevT
     }
 }
 
-__device__ __forceinline__ void emit_event(const Eng &G, int r, RepCtr *c, int32_t a, int type) {
-    uint32_t idx = atomicAdd(&c->n_events, 1u);
-    if (idx < G.cap_events) {
-        G.ev_key[(size_t)r * G.cap_events + idx] = ((unsigned long long)sweep_pos(G, c, (uint32_t)a) << 2) | (unsigned)type;
-        G.ev_agent[(size_t)r * G.cap_events + idx] = a;
-    } else set_problem(c, RB_OTHER_FAILURE);
+__device__ __forceinline__ void emit_event(const Eng &G, const SweepOut &O, RepCtr *c, int32_t a, int type) {
+    uint32_t idx = atomicAdd(&O.cd->n_events, 1u);
+    if (idx < O.cap_ev) {
+        O.ev_key[idx] = ((unsigned long long)sweep_pos(G, c, (uint32_t)a) << 2) | (unsigned)type;
+        O.ev_agent[idx] = a;
+    } else set_problem(O.cd, RB_OTHER_FAILURE);
 }
 
 // stage T: the state changes of person_advance (main.pyx:405-438) for agents whose day counter reached zero
-__device__ __forceinline__ void stage_transition(const Eng &G, int r, RepCtr *c, const WarpRings &W, uint32_t head, uint32_t m, int lane) {
-    if ((uint32_t)lane >= m) return;
+__device__ __forceinline__ void stage_transition_lane(const Eng &G, int r, RepCtr *c, const SweepOut &O, const WarpRings &W, uint32_t head, int lane,
+                                                      int32_t &a_out, uint32_t &h_out) {
+    RepCtr *cd = O.cd;
     const size_t base = (size_t)r * G.Npad;
     const int32_t a = (int32_t)W.ta[(head + lane) & (SW_RCAP - 1)];
     uint32_t h = W.tw[(head + lane) & (SW_RCAP - 1)];
@@ -772,24 +843,23 @@ __device__ __forceinline__ void stage_transition(const Eng &G, int r, RepCtr *c,
             }
             if (q && !(h & H_QUEUED)) {     // queue_for_testing guards (not DEAD / detected / queued), main.pyx:476
                 h |= H_QUEUED;
-                uint32_t idx = atomicAdd(&c->n_newq, 1u);
-                if (idx < G.cap_queue) {
-                    size_t qb = ((size_t)r * 2 + (c->qsel ^ 1u)) * G.cap_queue;
-                    G.q_key[qb + idx] = QKEY_SWEEP | sweep_pos(G, c, (uint32_t)a);
-                    G.q_agent[qb + idx] = a;
-                } else set_problem(c, RB_OTHER_FAILURE);
+                uint32_t idx = atomicAdd(&cd->n_newq, 1u);
+                if (idx < O.cap_q) {
+                    O.q_key[idx] = QKEY_SWEEP | sweep_pos(G, c, (uint32_t)a);
+                    O.q_agent[idx] = a;
+                } else set_problem(cd, RB_OTHER_FAILURE);
             }
         }
     } else if (st == RB_ILLNESS) {
         if (sev == RB_FATAL) {                       // person_die, main.pyx:370-374, 1618-1623
             h = H_SET_STATE(h, RB_DEAD) & ~H_LIST;
-            count_add(c, RB_A_INFECTED, age, -1); count_add(c, RB_A_DEAD, age, 1); count_add(c, RB_A_NON_HOSPITAL_DEATHS, age, 1);
+            count_add(cd, RB_A_INFECTED, age, -1); count_add(cd, RB_A_DEAD, age, 1); count_add(cd, RB_A_NON_HOSPITAL_DEATHS, age, 1);
         } else if (sev >= RB_SEVERE) {               // person_hospitalize, main.pyx:321-338: the bed claim is an event
-            if (!(h & H_DET)) { h |= H_DET; count_add(c, RB_A_DETECTED, age, 1); count_add(c, RB_A_ALL_DETECTED, age, 1); }
-            emit_event(G, r, c, a, EV_HOSP_CLAIM);
+            if (!(h & H_DET)) { h |= H_DET; count_add(cd, RB_A_DETECTED, age, 1); count_add(cd, RB_A_ALL_DETECTED, age, 1); }
+            emit_event(G, O, c, a, EV_HOSP_CLAIM);
         } else {                                     // person_recover, main.pyx:315-318
             h = H_SET_STATE(h, RB_RECOVERED) & ~H_LIST;
-            count_add(c, RB_A_INFECTED, age, -1); count_add(c, RB_A_RECOVERED, age, 1);
+            count_add(cd, RB_A_INFECTED, age, -1); count_add(cd, RB_A_RECOVERED, age, 1);
         }
     } else {   // HOSPITALIZED / IN_ICU
         int type;
@@ -797,18 +867,35 @@ __device__ __forceinline__ void stage_transition(const Eng &G, int r, RepCtr *c,
         else {
             // person_release_from_hospital, main.pyx:354-367: the outcome does not depend on capacity
             type = st == RB_IN_ICU ? EV_ICU_RELEASE : EV_WARD_RELEASE;
-            count_add(c, st == RB_IN_ICU ? RB_A_IN_ICU : RB_A_IN_WARD, age, -1);
-            count_add(c, RB_A_INFECTED, age, -1);
-            if (sev == RB_FATAL) { h = H_SET_STATE(h, RB_DEAD) & ~H_LIST; count_add(c, RB_A_DEAD, age, 1); count_add(c, RB_A_NON_HOSPITAL_DEATHS, age, 1); }
-            else { h = H_SET_STATE(h, RB_RECOVERED) & ~H_LIST; count_add(c, RB_A_RECOVERED, age, 1); }
+            count_add(cd, st == RB_IN_ICU ? RB_A_IN_ICU : RB_A_IN_WARD, age, -1);
+            count_add(cd, RB_A_INFECTED, age, -1);
+            if (sev == RB_FATAL) { h = H_SET_STATE(h, RB_DEAD) & ~H_LIST; count_add(cd, RB_A_DEAD, age, 1); count_add(cd, RB_A_NON_HOSPITAL_DEATHS, age, 1); }
+            else { h = H_SET_STATE(h, RB_RECOVERED) & ~H_LIST; count_add(cd, RB_A_RECOVERED, age, 1); }
         }
-        emit_event(G, r, c, a, type);
+        emit_event(G, O, c, a, type);
     }
     G.hot[base + a] = h;
+    a_out = a; h_out = h;
+}
+__device__ __forceinline__ void stage_transition(const Eng &G, int r, RepCtr *c, const WarpRings &W, uint32_t head, uint32_t m, int lane) {
+    const SweepOut O = sweep_out(G, r, c);     // resolved here, not in the caller: the streaming loop stays light on registers
+    int32_t a = 0; uint32_t h = 0;
+    const bool on = (uint32_t)lane < m;
+    if (on) stage_transition_lane(G, r, c, O, W, head, lane, a, h);
+    if (O.upd) {      // sharded mode: the other ranks' copies of this agent learn the new state and flags from the log
+        const uint32_t mk = __ballot_sync(0xffffffffu, on);
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(&O.cd->n_upd, (uint32_t)__popc(mk));
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (on) {
+            const uint32_t idx = b + __popc(mk & ((1u << lane) - 1u));
+            if (idx < O.cap_upd) O.upd[idx] = make_uint2((uint32_t)a, h); else set_problem(O.cd, RB_OTHER_FAILURE);
+        }
+    }
 }
 
 // stage 1 over one batch of ring A; pushes to rings E and T
-__device__ __forceinline__ void stage_active(const Eng &G, int r, RepCtr *c, WarpRings &W, uint32_t head, uint32_t m,
+__device__ __forceinline__ void stage_active(const Eng &G, int r, RepCtr *c, RepCtr *cd, WarpRings &W, uint32_t head, uint32_t m,
                                              uint32_t &e_tail, uint32_t &t_tail, int lane) {
     const size_t base = (size_t)r * G.Npad;
     bool want_e = false, want_t = false;
@@ -818,8 +905,8 @@ __device__ __forceinline__ void stage_active(const Eng &G, int r, RepCtr *c, War
         h = G.hot[base + a];               // the only per-agent gather of the sweep: ~3 % of the agents on an average day
         const uint32_t st = H_STATE(h);
         if (st >= RB_RECOVERED) {          // R bookkeeping, main.pyx:1969-1972 (only agents not yet included reach here)
-            atomicAdd(&c->total_infectors, 1);
-            atomicAdd(&c->total_infections, (int)(G.rec[base + a].cold & 0xffffu));
+            atomicAdd(&cd->total_infectors, 1);
+            atomicAdd(&cd->total_infections, (int)(G.rec[base + a].cold & 0xffffu));
             G.hot[base + a] = h | H_INCL;
             atomicAnd(&G.act[(size_t)r * G.sus_words + (a >> 5)], ~(1u << (a & 31)));   // nothing left to do for this agent
         } else if (h & H_FRESH) {          // infected today before the sweep: wait until tomorrow, main.pyx:402-403
@@ -845,7 +932,7 @@ __device__ __forceinline__ void stage_active(const Eng &G, int r, RepCtr *c, War
     t_tail = ring_push(W.ta, W.tw, t_tail, want_t, a, h, lane);
 }
 
-__global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
+__global__ void __launch_bounds__(SW_THREADS, 4) k_sweep(Eng G) {
     __shared__ WarpRings s_rings[SW_WARPS];
     const int r = blockIdx.y;
     RepCtr *c = &G.ctr[r];
@@ -855,17 +942,22 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
     uint2 *items = G.items + (size_t)r * G.cap_items;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpRings &W = s_rings[warp];
+    RepCtr *cd = !G.xbuf ? c : xslot_of(G, G.rank).hdr;      // counters the sweep adds to
     // One bit per agent says whether the sweep has anything to do for it (infected, or removed and not yet counted in
     // R), so the pass over all N agents reads 1/32 of the packed state -- an L2-resident bitmap -- and only the
-    // active agents' words are gathered.  A warp step covers 32 lanes x 128 agents.
+    // active agents' words are gathered.  A warp step covers 32 lanes x 128 agents = one ownership stripe.
     const int n_vec = G.sus_words >> 2;
+    const int nrk = G.nranks, rk = G.rank;
     uint32_t head = 0, tail = 0, e_head = 0, e_tail = 0, t_head = 0, t_tail = 0;
     if (c->stream_mode) {
         // dense day: coalesced 16-byte loads of the packed words themselves, 256 agents per warp step; the queued
         // agents' words are re-read in stage 1 from L1
         const uint4 *hot4 = reinterpret_cast<const uint4 *>(G.hot + base);
         const int n_chunks = (G.Npad + SW_CHUNK - 1) / SW_CHUNK, n4 = G.Npad >> 2;
-        for (int chunk = blockIdx.x * SW_WARPS + warp; chunk < n_chunks; chunk += gridDim.x * SW_WARPS) {
+        const int n_mine = (((n_chunks + 15) >> 4) + nrk - 1) / nrk * 16;      // this rank's chunks: 16 per stripe
+        for (int j = blockIdx.x * SW_WARPS + warp; j < n_mine; j += gridDim.x * SW_WARPS) {
+            const int chunk = nrk == 1 ? j : ((((j >> 4) * nrk + rk) << 4) | (j & 15));
+            if (chunk >= n_chunks) continue;
             const int a0 = chunk * SW_CHUNK;
             const int i0 = (a0 >> 2) + lane, i1 = i0 + 32;
             uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
@@ -874,9 +966,9 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
             const uint32_t hw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
             uint32_t act = 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                uint32_t st = H_STATE(hw[j]);
-                if (st != RB_SUSCEPTIBLE && !(st >= RB_RECOVERED && (hw[j] & H_INCL))) act |= 1u << j;
+            for (int j2 = 0; j2 < 8; j2++) {
+                uint32_t st = H_STATE(hw[j2]);
+                if (st != RB_SUSCEPTIBLE && !(st >= RB_RECOVERED && (hw[j2] & H_INCL))) act |= 1u << j2;
             }
             if (!__any_sync(0xffffffffu, act != 0)) continue;
             uint32_t mine = __popc(act), incl = mine;
@@ -885,20 +977,23 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
             const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
             uint32_t p = tail + incl - mine;
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (act & (1u << j)) { W.qi[p & (SW_QCAP - 1)] = (uint32_t)(a0 + (j < 4 ? lane * 4 + j : 128 + lane * 4 + (j - 4))); p++; }
+            for (int j2 = 0; j2 < 8; j2++)
+                if (act & (1u << j2)) { W.qi[p & (SW_QCAP - 1)] = (uint32_t)(a0 + (j2 < 4 ? lane * 4 + j2 : 128 + lane * 4 + (j2 - 4))); p++; }
             tail += tot;
             __syncwarp();
             while (tail - head >= 32) {
-                stage_active(G, r, c, W, head, 32, e_tail, t_tail, lane); head += 32;
+                stage_active(G, r, c, cd, W, head, 32, e_tail, t_tail, lane); head += 32;
                 __syncwarp();
-                if (e_tail - e_head >= 32) { stage_expose(G, c, tb, W, e_head, 32, items, lane); e_head += 32; }
+                if (e_tail - e_head >= 32) { stage_expose(G, c, cd, tb, W, e_head, 32, items, lane); e_head += 32; }
                 if (t_tail - t_head >= 32) { stage_transition(G, r, c, W, t_head, 32, lane); t_head += 32; }
                 __syncwarp();
             }
         }
-    } else
-    for (int v0 = (blockIdx.x * SW_WARPS + warp) * 32; v0 < n_vec; v0 += gridDim.x * SW_WARPS * 32) {
+    } else {
+    const int n_steps = (n_vec + 31) >> 5, n_mine = (n_steps + nrk - 1) / nrk;
+    for (int j = blockIdx.x * SW_WARPS + warp; j < n_mine; j += gridDim.x * SW_WARPS) {
+        const int v0 = (nrk == 1 ? j : j * nrk + rk) * 32;
+        if (v0 >= n_vec) continue;
         const int vi = v0 + lane;
         uint4 bits = make_uint4(0, 0, 0, 0);
         if (vi < n_vec) bits = __ldg(&act4[vi]);
@@ -924,19 +1019,20 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
                 __syncwarp();
                 while (tail - head >= 32) {
                     if (G.dbg == 3) { head += 32; continue; }
-                    stage_active(G, r, c, W, head, 32, e_tail, t_tail, lane); head += 32;
+                    stage_active(G, r, c, cd, W, head, 32, e_tail, t_tail, lane); head += 32;
                     __syncwarp();
-                    if (e_tail - e_head >= 32) { if (G.dbg != 1) stage_expose(G, c, tb, W, e_head, 32, items, lane); e_head += 32; }
+                    if (e_tail - e_head >= 32) { if (G.dbg != 1) stage_expose(G, c, cd, tb, W, e_head, 32, items, lane); e_head += 32; }
                     if (t_tail - t_head >= 32) { if (G.dbg != 2) stage_transition(G, r, c, W, t_head, 32, lane); t_head += 32; }
                     __syncwarp();
                 }
             }
         }
     }
+    }
     // drain: whatever is left in ring A, then rings E and T (at most two partial batches each)
-    if (tail != head) { stage_active(G, r, c, W, head, tail - head, e_tail, t_tail, lane); }
+    if (tail != head) { stage_active(G, r, c, cd, W, head, tail - head, e_tail, t_tail, lane); }
     __syncwarp();
-    while (e_tail != e_head) { uint32_t m = min(32u, e_tail - e_head); stage_expose(G, c, tb, W, e_head, m, items, lane); e_head += m; }
+    while (e_tail != e_head) { uint32_t m = min(32u, e_tail - e_head); stage_expose(G, c, cd, tb, W, e_head, m, items, lane); e_head += m; }
     while (t_tail != t_head) { uint32_t m = min(32u, t_tail - t_head); stage_transition(G, r, c, W, t_head, m, lane); t_head += m; }
 }
 
@@ -950,8 +1046,8 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(Eng G) {
 #define EX_WARPS (EX_THREADS / 32)
 #define EX_RCAP 256
 
-__device__ __forceinline__ void expose_survivors(const Eng &G, int r, RepCtr *c, const DevTable *tb, const uint2 *items, const uint32_t *sus,
-                                                 Attempt *succ, const uint32_t *ri, const uint32_t *rx, uint32_t head, uint32_t m, int lane) {
+__device__ __forceinline__ void expose_survivors(const Eng &G, int r, RepCtr *c, RepCtr *cd, const DevTable *tb, const uint2 *items, const uint32_t *sus,
+                                                 Attempt *succ, uint32_t cap_succ, const uint32_t *ri, const uint32_t *rx, uint32_t head, uint32_t m, int lane) {
     if ((uint32_t)lane >= m) return;
     const size_t base = (size_t)r * G.Npad;
     const uint2 it = items[ri[(head + lane) & (EX_RCAP - 1)]];
@@ -977,9 +1073,11 @@ __device__ __forceinline__ void expose_survivors(const Eng &G, int r, RepCtr *c,
         if (chance((double)y.z * (1.0 / 4294967296.0), pm)) return;
     }
     const unsigned long long key = ((unsigned long long)sweep_pos(G, c, a) << 7) | slot;
-    const uint32_t idx = atomicAdd(&c->n_succ, 1u);
-    if (idx < G.cap_succ) { succ[idx].cand = t; succ[idx].parent = a; succ[idx].key = key; atomicMin(&G.rec[base + t].winner, key); }
-    else set_problem(c, RB_OTHER_FAILURE);
+    const uint32_t idx = atomicAdd(&cd->n_succ, 1u);
+    if (idx < cap_succ) {
+        succ[idx].cand = t; succ[idx].parent = a; succ[idx].key = key;
+        if (!G.xbuf) atomicMin(&G.rec[base + t].winner, key);     // sharded: k_merge does it over every rank's list
+    } else set_problem(cd, RB_OTHER_FAILURE);
 }
 
 __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
@@ -994,6 +1092,9 @@ __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
     __syncthreads();
     const uint2 *items = G.items + (size_t)r * G.cap_items;
     Attempt *succ = G.succ + (size_t)r * G.cap_succ;
+    uint32_t cap_succ = G.cap_succ;
+    RepCtr *cd = c;
+    if (G.xbuf) { const XSlot x = xslot_of(G, G.rank); succ = x.succ; cap_succ = G.xcap_succ; cd = x.hdr; }
     const uint32_t *sus = G.sus + (size_t)r * G.sus_words;
     const uint32_t day = (uint32_t)c->day;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1041,7 +1142,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
             tail += __popc(m);
         }
         __syncwarp();
-        while (tail - head >= 32) { expose_survivors(G, r, c, tb, items, sus, succ, ri, rx, head, 32, lane); head += 32; }
+        while (tail - head >= 32) { expose_survivors(G, r, c, cd, tb, items, sus, succ, cap_succ, ri, rx, head, 32, lane); head += 32; }
         __syncwarp();
         if (++since_flush == 7) {        // 7 iterations x 4 contacts = 28 < 32 fits the 5-bit fields
 #pragma unroll
@@ -1049,11 +1150,72 @@ __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
             places = 0; since_flush = 0;
         }
     }
-    if (tail != head) expose_survivors(G, r, c, tb, items, sus, succ, ri, rx, head, tail - head, lane);
+    if (tail != head) expose_survivors(G, r, c, cd, tb, items, sus, succ, cap_succ, ri, rx, head, tail - head, lane);
 #pragma unroll
     for (int pl = 0; pl < RB_N_PLACES; pl++) { const uint32_t k = (places >> (5 * pl)) & 31u; if (k) atomicAdd(&s_place[pl], (int)k); }
     __syncthreads();
-    if (threadIdx.x < RB_N_PLACES && s_place[threadIdx.x]) atomicAdd(&c->daily_contacts[threadIdx.x], s_place[threadIdx.x]);
+    if (threadIdx.x < RB_N_PLACES && s_place[threadIdx.x]) atomicAdd(&cd->daily_contacts[threadIdx.x], s_place[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------- k_merge (population-sharded mode only)
+// After the all-gather every rank holds every rank's message.  All ranks apply all of them in rank order, so the
+// replicated state (counters, test queue, capacity events, packed words, conflict slots) stays identical everywhere:
+// count deltas are added, queue entries / events / successful transmissions are concatenated into the single-GPU
+// lists, the other ranks' state changes overwrite the local copies of their agents, and every successful
+// transmission does its atomicMin on the target's conflict slot (first infector in sweep order wins, main.pyx:238-244).
+#define MAX_RANKS 16
+__global__ void __launch_bounds__(256) k_merge(Eng G) {
+    __shared__ uint32_t nq[MAX_RANKS + 1], ne[MAX_RANKS + 1], nu[MAX_RANKS + 1], ns[MAX_RANKS + 1];
+    RepCtr *c = &G.ctr[0];
+    const int nrk = G.nranks;
+    if (threadIdx.x == 0) {
+        uint32_t q = 0, e = 0, u = 0, sx = 0;
+        for (int k = 0; k < nrk; k++) {
+            const RepCtr *h = xslot_of(G, k).hdr;
+            nq[k] = q; ne[k] = e; nu[k] = u; ns[k] = sx;
+            q += min(h->n_newq, G.xcap_q); e += min(h->n_events, G.xcap_ev); u += min(h->n_upd, G.xcap_upd); sx += min(h->n_succ, G.xcap_succ);
+        }
+        nq[nrk] = q; ne[nrk] = e; nu[nrk] = u; ns[nrk] = sx;
+    }
+    __syncthreads();
+    const uint32_t qbase = c->n_q_base;
+    const size_t qb = (size_t)(c->qsel ^ 1u) * G.cap_queue;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int k = 0; k < nrk; k++) {
+        const XSlot x = xslot_of(G, k);
+        for (uint32_t i = gtid; i < nq[k + 1] - nq[k]; i += gsz) {
+            const uint32_t d = qbase + nq[k] + i;
+            if (d < G.cap_queue) { G.q_key[qb + d] = x.q_key[i]; G.q_agent[qb + d] = x.q_agent[i]; }
+        }
+        for (uint32_t i = gtid; i < ne[k + 1] - ne[k]; i += gsz) {
+            const uint32_t d = ne[k] + i;
+            if (d < G.cap_events) { G.ev_key[d] = x.ev_key[i]; G.ev_agent[d] = x.ev_agent[i]; }
+        }
+        if (k != G.rank)
+            for (uint32_t i = gtid; i < nu[k + 1] - nu[k]; i += gsz) { const uint2 u = x.upd[i]; G.hot[u.x] = u.y; }
+        for (uint32_t i = gtid; i < ns[k + 1] - ns[k]; i += gsz) {
+            const uint32_t d = ns[k] + i;
+            if (d < G.cap_succ) { const Attempt at = x.succ[i]; G.succ[d] = at; atomicMin(&G.rec[at.cand].winner, at.key); }
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < RB_N_ATTRS * RB_MAX_AGES; i += blockDim.x) {
+            int d = 0;
+            for (int k = 0; k < nrk; k++) d += (&xslot_of(G, k).hdr->counts[0][0])[i];
+            if (d) (&c->counts[0][0])[i] += d;
+        }
+        if (threadIdx.x < RB_N_PLACES) { int d = 0; for (int k = 0; k < nrk; k++) d += xslot_of(G, k).hdr->daily_contacts[threadIdx.x]; c->daily_contacts[threadIdx.x] += d; }
+        if (threadIdx.x == 32) {
+            for (int k = 0; k < nrk; k++) {
+                const RepCtr *h = xslot_of(G, k).hdr;
+                c->total_infectors += h->total_infectors; c->total_infections += h->total_infections; c->exposed_per_day += h->exposed_per_day;
+                if (h->problem) set_problem(c, h->problem);
+                if (h->n_newq > G.xcap_q || h->n_events > G.xcap_ev || h->n_upd > G.xcap_upd || h->n_succ > G.xcap_succ) set_problem(c, RB_OTHER_FAILURE);
+            }
+            if (qbase + nq[nrk] > G.cap_queue || ne[nrk] > G.cap_events || ns[nrk] > G.cap_succ) set_problem(c, RB_OTHER_FAILURE);
+            c->n_newq = min(qbase + nq[nrk], G.cap_queue); c->n_events = min(ne[nrk], G.cap_events); c->n_succ = min(ns[nrk], G.cap_succ);
+        }
+    }
 }
 
 // ---------------------------------------------------------------- k_resolve
@@ -1281,7 +1443,40 @@ struct rb_engine {
     int sweep_blocks, list_blocks, resolve_blocks;
     cudaGraphExec_t graph[2];
     bool have_graphs;
+    ncclComm_t comm;                    // population-sharded mode
+    int merge_blocks;
 };
+
+// ---------------------------------------------------------------- NCCL, bound at run time
+struct NcclApi {
+    void *dl;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    const char *(*GetErrorString)(ncclResult_t);
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.dl) return 0;
+    // reuse a libnccl the process already mapped (torch ships one with the same soname), else load the system one
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { snprintf(g_err, sizeof g_err, "cannot load libnccl.so.2: %s", dlerror()); return 1; }
+    g_nccl.GetUniqueId = (ncclResult_t(*)(ncclUniqueId *))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (ncclResult_t(*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllGather = (ncclResult_t(*)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.CommDestroy = (ncclResult_t(*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(ncclResult_t))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy || !g_nccl.GetErrorString) {
+        snprintf(g_err, sizeof g_err, "libnccl.so.2 lacks a required symbol"); return 1;
+    }
+    g_nccl.dl = h;
+    return 0;
+}
+#define NK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { snprintf(g_err, sizeof g_err, "%s:%d %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); return 1; } } while (0)
+
 
 template <typename T> static int dalloc(rb_engine *e, T **p, size_t n) {
     void *q = nullptr;
@@ -1320,6 +1515,7 @@ extern "C" void rb_destroy(rb_engine *e) {
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     if (e->have_graphs) { cudaGraphExecDestroy(e->graph[0]); cudaGraphExecDestroy(e->graph[1]); }
+    if (e->comm) g_nccl.CommDestroy(e->comm);
     for (void *p : e->allocs) cudaFree(p);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaStreamDestroy(e->stream);
@@ -1339,7 +1535,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     }
     CK(cudaSetDevice(cfg->device));
     rb_engine *e = new rb_engine();
-    e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0; e->have_graphs = false;
+    e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0; e->have_graphs = false; e->comm = nullptr; e->merge_blocks = 1;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     Eng &G = e->G;
@@ -1348,6 +1544,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     G.N = N; G.Npad = (N + 3) & ~3; G.n_ages = cfg->n_ages; G.n_groups = cfg->n_groups; G.n_variants = cfg->n_variants;
     G.R = R; G.max_days = cfg->max_days; G.row_len = RB_N_ATTRS * cfg->n_groups + RB_N_SCALARS;
     G.n_import_classes = cfg->n_import_classes;
+    G.rank = 0; G.nranks = 1;
     int bits = 1; while ((1u << bits) < (uint32_t)N) bits++;
     G.fhalf = (bits + 1) / 2;
     e->age_start.resize(cfg->n_ages + 1);
@@ -1510,6 +1707,62 @@ static int build_graphs(rb_engine *e) {
     return 0;
 }
 
+// ---------------------------------------------------------------- population-sharded mode
+extern "C" int rb_shard_unique_id(uint8_t *out128) {
+    if (load_nccl()) return 1;
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(out128, &id, 128);
+    return 0;
+}
+
+extern "C" int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const uint8_t *uid128, float exchange_capacity) {
+    if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) { snprintf(g_err, sizeof g_err, "bad rank %d / %d", rank, nranks); return 1; }
+    if (e->G.R != 1) { snprintf(g_err, sizeof g_err, "population-sharded mode runs one replica (n_replicas = %d)", e->G.R); return 1; }
+    if (e->day != 0 || e->comm) { snprintf(g_err, sizeof g_err, "rb_shard_init must be the first call after rb_create"); return 1; }
+    if (load_nccl()) return 1;
+    CK(cudaSetDevice(e->cfg.device));
+    ncclUniqueId id; memcpy(&id, uid128, 128);
+    NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
+    Eng &G = e->G;
+    // message capacities: this rank's share of the agents; a day's state changes / transmissions / tests / capacity
+    // events are small fractions of it (peak of the reference epidemic: ~1.3 % / 0.5 % / 0.2 % / 0.02 % of the agents)
+    const double share = (double)G.N / nranks * (exchange_capacity > 0 ? exchange_capacity : 1.0);
+    G.xcap_upd = (uint32_t)(share / 16) + 4096;
+    G.xcap_succ = (uint32_t)(share / 48) + 4096;
+    G.xcap_q = (uint32_t)(share / 64) + 2048;
+    G.xcap_ev = (uint32_t)(share / 256) + 2048;
+    G.xslot = xslot_bytes(G.xcap_q, G.xcap_ev, G.xcap_upd, G.xcap_succ);
+    if (dalloc(e, &G.xbuf, G.xslot * nranks)) return 1;
+    CK(cudaMemset(G.xbuf, 0, G.xslot * nranks));
+    G.rank = rank; G.nranks = nranks;
+    int sb = (e->sweep_blocks + nranks - 1) / nranks; if (sb < 1) sb = 1;
+    e->sweep_blocks = sb;
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, e->cfg.device));
+    e->merge_blocks = prop.multiProcessorCount * 2;
+    return 0;
+}
+
+extern "C" int32_t rb_shard_rank(rb_engine *e) { return e->G.rank; }
+extern "C" int32_t rb_shard_nranks(rb_engine *e) { return e->G.nranks; }
+extern "C" int64_t rb_shard_message_bytes(rb_engine *e) { return e->comm ? (int64_t)e->G.xslot : 0; }
+
+// One simulated day in sharded mode: sweep and contacts over the owned stripes, ONE all-gather of the ranks' messages,
+// then merge / resolve / day boundary replicated on every rank.
+static int launch_day_sharded(rb_engine *e, bool last) {
+    const Eng &G = e->G;
+    cudaStream_t st = e->stream;
+    k_sweep<<<dim3(e->sweep_blocks, 1), SW_THREADS, 0, st>>>(G);
+    k_expose<<<dim3(e->list_blocks, 1), EX_THREADS, 0, st>>>(G);
+    NK(g_nccl.AllGather(G.xbuf + (size_t)G.rank * G.xslot, G.xbuf, G.xslot, ncclChar, e->comm, st));
+    k_merge<<<e->merge_blocks, 256, 0, st>>>(G);
+    k_resolve<<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G);
+    if (last) k_post<<<1, PRE_THREADS, 0, st>>>(G); else k_between<<<1, PRE_THREADS, 0, st>>>(G);
+    e->launches += 5;
+    return 0;
+}
+
 extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     CK(cudaSetDevice(e->cfg.device));
     if (n_days <= 0) return 0;
@@ -1518,9 +1771,18 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
         int ep = e->h_sched[e->day + d].table_epoch;
         if (ep < 0 || ep >= e->n_table_slots || !e->tables[ep]) { snprintf(g_err, sizeof g_err, "contact table %d not set", ep); return 1; }
     }
-    if (!e->have_graphs && build_graphs(e)) return 1;
+    if (!e->comm && !e->have_graphs && build_graphs(e)) return 1;
     const Eng &G = e->G;
     const int R = G.R;
+    if (e->comm) {
+        CK(cudaEventRecord(e->ev0, e->stream));
+        k_pre<<<1, PRE_THREADS, 0, e->stream>>>(G); e->launches++;
+        for (int d = 0; d < n_days; d++) if (launch_day_sharded(e, d == n_days - 1)) return 1;
+        CK(cudaEventRecord(e->ev1, e->stream));
+        CK(cudaGetLastError());
+        e->day += n_days;
+        return 0;
+    }
     CK(cudaEventRecord(e->ev0, e->stream));
     k_pre<<<R, PRE_THREADS, 0, e->stream>>>(G); e->launches++;
     int mid = n_days - 1;
@@ -1540,6 +1802,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
 extern "C" int rb_step_profiled(rb_engine *e, int32_t n_days, float *ms_per_kernel) {
     CK(cudaSetDevice(e->cfg.device));
     if (e->day + n_days > e->cfg.max_days) { snprintf(g_err, sizeof g_err, "max_days exceeded"); return 1; }
+    if (e->comm) { snprintf(g_err, sizeof g_err, "rb_step_profiled: not available in population-sharded mode"); return 1; }
     const Eng &G = e->G;
     const int R = G.R;
     std::vector<cudaEvent_t> ev((size_t)n_days * 6);

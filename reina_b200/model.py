@@ -244,7 +244,7 @@ class Context:
 
     def __init__(self, population_params, healthcare_params, disease_params, start_date,
                  random_seed=4321, n_replicas=1, device=0, max_days=600, contact_capacity=0.0,
-                 _library=None):
+                 shard=None, _library=None):
         lib = _library if _library is not None else _abi.cuda_library()
         ipc = population_params.pop('initial_population_condition', None)   # main.pyx:1765 (mutates, as the reference)
         if ipc is not None and getattr(ipc, 'has_initial_state', lambda: False)():
@@ -298,6 +298,10 @@ class Context:
         cfg.max_days, cfg.n_import_classes, cfg.device = int(max_days), len(lo), int(device)
         cfg.contact_capacity = float(contact_capacity)
         self._engine = _abi.Engine(lib, cfg, age_counts, group_of_age[:n_ages], variants, lo, hi, cum)
+        if shard is not None:
+            # population-sharded mode: shard = (rank, nranks, nccl_unique_id[, exchange_capacity]); every rank builds the
+            # same Context (same inputs, interventions and seed) on its own GPU and makes the same calls
+            self._engine.shard_init(int(shard[0]), int(shard[1]), shard[2], float(shard[3]) if len(shard) > 3 else 0.0)
 
         self.n_agents, self.n_ages, self.n_replicas = n_agents, n_ages, int(n_replicas)
         self.max_days = int(max_days)

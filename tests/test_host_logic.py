@@ -13,11 +13,27 @@ from reina_b200 import _abi, inputs, model
 def test_libraries_export_every_declared_symbol():
     hdr = open(os.path.join(helpers.ROOT, 'include', 'reina_b200.h')).read()
     declared = sorted(set(re.findall(r'\brb_([a-z_]+)\s*\(', hdr)))
-    assert set(declared) == set(_abi.SYMBOLS), set(declared) ^ set(_abi.SYMBOLS)
+    assert set(declared) == set(_abi.SYMBOLS) | set(_abi.SHARD_SYMBOLS), set(declared) ^ (set(_abi.SYMBOLS) | set(_abi.SHARD_SYMBOLS))
     cuda = _abi.Library(_abi.CUDA_LIB_PATH, 'rb_')          # loads without a GPU; no compute call is made
     orac = helpers.oracle_library()
     for name in declared:
-        assert hasattr(cuda.dll, 'rb_' + name) and hasattr(orac.dll, 'ro_' + name), name
+        assert hasattr(cuda.dll, 'rb_' + name), name
+        # the multi-GPU entry points have no counterpart in the sequential CPU oracle
+        assert name in _abi.SHARD_SYMBOLS or hasattr(orac.dll, 'ro_' + name), name
+
+
+def test_shard_ownership_is_a_balanced_partition():
+    """Stripes of 4096 age-sorted agents dealt round-robin: every agent has exactly one owner and every rank
+    holds close to 1/nranks of every age decade (what keeps the per-rank sweep work balanced)."""
+    counts = inputs.synthetic_age_counts(1685983)
+    age_of = np.repeat(np.arange(len(counts)), counts)
+    for nranks in (1, 2, 4, 8):
+        owner = _abi.owner_of(np.arange(age_of.size), nranks)
+        assert owner.min() == 0 and owner.max() == nranks - 1
+        for decade in range(9):
+            sel = (age_of // 10 == decade) if decade < 8 else (age_of >= 80)
+            share = np.bincount(owner[sel], minlength=nranks) / sel.sum()
+            assert np.abs(share - 1.0 / nranks).max() < 0.05, (nranks, decade, share)
 
 
 def test_no_cpu_fallback(tmp_path):
