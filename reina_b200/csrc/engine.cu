@@ -90,24 +90,39 @@ struct __align__(32) AgentRec {
     int16_t vacc_day, pad;
 };
 
+// Per-replica counters.  The scalars the grid kernels hammer with atomics each sit on their own 128-byte line, away
+// from the fields every thread only READS (seed, day, sweep start ...): with one big replica all SMs share this one
+// struct, and a read that lands on a line with a queue of atomics in front of it waits for all of them.
 struct RepCtr {
     int32_t counts[RB_N_ATTRS][RB_MAX_AGES];
-    int32_t daily_contacts[RB_N_PLACES];
-    int32_t by_variant[RB_MAX_VARIANTS];
-    int32_t beds, icu, avail_beds, avail_icu;
-    int32_t total_infectors, total_infections, exposed_per_day, ct_cases;
+    // ---- written by the day-boundary CTA only, read by everybody
+    alignas(128) int32_t beds;
+    int32_t icu, avail_beds, avail_icu;
     int32_t problem, epoch, testing_mode, day;
     float p_detected_anyway, p_successful_tracing;
     uint32_t seed, start;
     uint32_t fkey[4];
-    uint32_t n_items, n_succ, n_events, n_queue, n_newq, qsel;
+    uint32_t n_queue, qsel;
     uint32_t n_queue_prev;                        // size of the queue drained yesterday (normalises tracing keys for sorting)
     uint32_t any_vacc;                            // set once the first vaccination programme starts
-    uint32_t n_l0, n_l1, n_edges, stream_mode;   // stream_mode: today's sweep streams the packed words instead of the activity bitmap
-    int32_t vacc_cursor[RB_MAX_VACC];
-    uint32_t n_upd;                               // population-sharded mode: packed-word updates logged by today's sweep
+    uint32_t stream_mode;                         // today's sweep streams the packed words instead of the activity bitmap
     uint32_t n_q_base;                            // entries contact tracing put into tomorrow's queue before the sweep
-    int32_t pad[4];
+    uint32_t drained;                             // tomorrow's queue was already drained by k_resolve (detections parked in drain_det)
+    int32_t ct_cases;
+    int32_t vacc_cursor[RB_MAX_VACC];
+    // ---- atomics of the grid kernels, one line per group
+    alignas(128) uint32_t n_items;
+    alignas(128) uint32_t n_succ;
+    alignas(128) int32_t exposed_per_day;
+    int32_t total_infectors, total_infections;
+    alignas(128) uint32_t n_events;
+    uint32_t n_newq;
+    uint32_t n_upd;                               // population-sharded mode: packed-word updates logged by today's sweep
+    alignas(128) int32_t daily_contacts[RB_N_PLACES];
+    int32_t by_variant[RB_MAX_VARIANTS];
+    alignas(128) int32_t drain_det[RB_MAX_AGES];  // detections of an early queue drain, per age, booked at the next day boundary
+    alignas(128) uint32_t n_l0;
+    uint32_t n_l1, n_edges;
     long long dbg_t[16];                          // measurement aid: cycles spent per phase of the day-boundary kernel
     long long dbg_last;
 };
@@ -248,7 +263,11 @@ __device__ void device_infect(const Eng &G, int r, RepCtr *c, int32_t t, int32_t
     count_add(c, RB_A_INFECTED, age, 1);
     count_add(c, RB_A_ALL_INFECTED, age, 1);
     count_add(c, RB_A_NEW_INFECTIONS, age, 1);
-    atomicAdd(&c->by_variant[variant], 1);
+    {   // infected_by_variant: one atomic per group of converged lanes with the same variant
+        const unsigned act = __activemask();
+        const unsigned grp = __match_any_sync(act, variant);
+        if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&c->by_variant[variant], __popc(grp));
+    }
 }
 
 // ---------------------------------------------------------------- block-wide helpers (single CTA)
@@ -316,46 +335,53 @@ __device__ int block_scan_incl(int v, int *total, int *warp_sums) {
 
 // Order-preserving bucket function for the two kinds of sort keys: capacity events (sweep position << 2 | type) and
 // test-queue entries (contact-tracing attempt keys first, then QKEY_SWEEP | sweep position).  Sweep positions are a
-// keyed permutation, so buckets receive ~n/2048 elements each.
-#define SORT_BUCKETS 2048
-struct BucketMap { uint32_t n_agents, n_prev; int kind; };     // kind 0: events, 1: queue
+// keyed permutation, so B buckets receive ~n/B elements each.
+#define SORT_BUCKETS 2048          // bucket counters in shared memory up to here, in global scratch beyond
+#define SORT_BUCKETS_MAX 65536
+struct BucketMap { uint32_t n_agents, n_prev; int kind; uint32_t B; };     // kind 0: events, 1: queue
 __device__ __forceinline__ uint32_t bucket_of(const BucketMap &bm, unsigned long long key) {
-    if (bm.kind == 0) return (uint32_t)(((key >> 2) * SORT_BUCKETS) / bm.n_agents);
-    if (key & QKEY_SWEEP) return SORT_BUCKETS / 2 + (uint32_t)(((key & 0xffffffffull) * (SORT_BUCKETS / 2)) / bm.n_agents);
+    if (bm.kind == 0) return (uint32_t)(((key >> 2) * bm.B) / bm.n_agents);
+    if (key & QKEY_SWEEP) return bm.B / 2 + (uint32_t)(((key & 0xffffffffull) * (bm.B / 2)) / bm.n_agents);
     unsigned long long i = key >> 14;                          // queue rank of the tracer, < n_prev
-    return (uint32_t)((i * (SORT_BUCKETS / 2)) / (bm.n_prev ? bm.n_prev : 1u));
+    return (uint32_t)((i * (bm.B / 2)) / (bm.n_prev ? bm.n_prev : 1u));
 }
 
-// Ascending sort of n (key, val) pairs with distinct keys by one CTA: counting sort into SORT_BUCKETS order-preserving
-// buckets (shared-memory histogram + scan), then each bucket is put in order by one thread.  O(n) for the uniformly
-// spread keys of this engine; `scratch` needs 2 n entries.  Returns false if the scratch area is too small.
+// Ascending sort of n (key, val) pairs with distinct keys by one CTA: counting sort into B ~ n order-preserving
+// buckets (histogram + scan), then each bucket (usually 0-2 elements) is put in order by one thread.  O(n) for the
+// uniformly spread keys of this engine; `scratch` needs 2 n entries plus B counters.  Returns false if it is too small.
 __device__ bool block_bucket_sort(unsigned long long *keys, int32_t *vals, uint32_t n, Attempt *scratch, uint32_t scratch_cap,
-                                  const BucketMap &bm, int32_t *cnt /* shared [SORT_BUCKETS] */, int *warp_sums) {
-    if (2ull * n > scratch_cap) return false;
+                                  BucketMap bm, int32_t *scnt /* shared [SORT_BUCKETS] */, int *warp_sums) {
+    uint32_t B = SORT_BUCKETS;
+    while (B < n && B < SORT_BUCKETS_MAX) B <<= 1;
+    if (2ull * n + B / 4 + 1 > scratch_cap) return false;
+    bm.B = B;
+    int32_t *cnt = B == SORT_BUCKETS ? scnt : (int32_t *)(scratch + 2ull * n);
     const int tid = threadIdx.x;
-    for (int b = tid; b < SORT_BUCKETS; b += blockDim.x) cnt[b] = 0;
+    for (uint32_t b = tid; b < B; b += blockDim.x) cnt[b] = 0;
     __syncthreads();
     for (uint32_t i = tid; i < n; i += blockDim.x) {
         const unsigned long long k = keys[i];
-        const uint32_t b = min(bucket_of(bm, k), (uint32_t)SORT_BUCKETS - 1u);
+        const uint32_t b = min(bucket_of(bm, k), B - 1u);
         const uint32_t slot = (uint32_t)atomicAdd(&cnt[b], 1);
-        scratch[i].key = k; scratch[i].cand = (uint32_t)vals[i]; scratch[i].parent = b | (slot << 11);
+        scratch[i].key = k; scratch[i].cand = (uint32_t)vals[i]; scratch[i].parent = b | (slot << 16);
     }
     __syncthreads();
-    // exclusive scan of the bucket counts: two buckets per thread
-    const int c0 = tid * 2 < SORT_BUCKETS ? cnt[tid * 2] : 0, c1 = tid * 2 + 1 < SORT_BUCKETS ? cnt[tid * 2 + 1] : 0;
+    // exclusive scan of the bucket counts: B / blockDim consecutive buckets per thread
+    const uint32_t per = B / blockDim.x, b0 = tid * per;
+    int mine = 0;
+    for (uint32_t j = 0; j < per; j++) mine += cnt[b0 + j];
     int total;
-    const int incl = block_scan_incl(c0 + c1, &total, warp_sums);
-    if (tid * 2 < SORT_BUCKETS) { cnt[tid * 2] = incl - c0 - c1; cnt[tid * 2 + 1] = incl - c1; }
+    int run = block_scan_incl(mine, &total, warp_sums) - mine;
+    for (uint32_t j = 0; j < per; j++) { const int v = cnt[b0 + j]; cnt[b0 + j] = run; run += v; }
     __syncthreads();
     Attempt *out = scratch + n;
     for (uint32_t i = tid; i < n; i += blockDim.x) {
         const Attempt e = scratch[i];
-        out[cnt[e.parent & (SORT_BUCKETS - 1)] + (e.parent >> 11)] = e;
+        out[cnt[e.parent & 0xffffu] + (e.parent >> 16)] = e;
     }
     __syncthreads();
-    for (int b = tid; b < SORT_BUCKETS; b += blockDim.x) {      // insertion sort inside each bucket (usually 0-2 elements)
-        const uint32_t lo = (uint32_t)cnt[b], hi = b + 1 < SORT_BUCKETS ? (uint32_t)cnt[b + 1] : n;
+    for (uint32_t b = tid; b < B; b += blockDim.x) {      // insertion sort inside each bucket
+        const uint32_t lo = (uint32_t)cnt[b], hi = b + 1 < B ? (uint32_t)cnt[b + 1] : n;
         for (uint32_t i = lo + 1; i < hi; i++) {
             const Attempt e = out[i];
             uint32_t j = i;
@@ -397,32 +423,42 @@ __device__ void write_stats_row(const Eng &G, int r, RepCtr *c, int32_t *srow /*
 
 // Population.infect_people + get_import_infection_person, main.pyx:1632-1665.  Sequential semantics: import j takes
 // the first of its (up to 10) draws that is SUSCEPTIBLE and was not taken by an earlier import of the same day.
-// All draws of up to IMP_CHUNK imports are evaluated in parallel, one thread settles the order-dependent choice from
-// shared memory, then the chosen people are infected in parallel.  Called by the whole CTA.
-#define IMP_CHUNK 96
-__device__ void import_infections(const Eng &G, int r, RepCtr *c, int count, int variant, int *ordinal, int32_t *cand /*[IMP_CHUNK*10]*/,
-                                  int32_t *chosen /*[IMP_CHUNK]*/) {
+// Up to IMP_CHUNK imports are settled at once, one per thread: each takes its first susceptible draw; if all picks
+// of the chunk are distinct (checked through the agents' conflict slots) that IS the sequential result, otherwise
+// (probability ~ chunk^2 / N) one thread replays the chunk in order.  Called by the whole CTA.
+#define IMP_CHUNK 1024
+__device__ __forceinline__ int32_t import_draw(const Eng &G, const RepCtr *c, size_t base, uint32_t ord, uint32_t t) {
+    u32x4 x = philox(c->seed, ord, (uint32_t)c->day, PU_IMPORT | (t << 8), 0);
+    float p = u01f(x.x);
+    int k = G.n_import_classes - 1;
+    for (int j = 0; j < G.n_import_classes; j++) if (p <= G.import_cum[j]) { k = j; break; }
+    int32_t s = G.age_start[G.import_lo[k]], en = G.age_start[G.import_hi[k] + 1];
+    int32_t pi = s + (int32_t)(x.y % (uint32_t)(en - s));
+    return H_STATE(G.hot[base + pi]) == RB_SUSCEPTIBLE ? pi : -1;
+}
+__device__ void import_infections(const Eng &G, int r, RepCtr *c, int count, int variant, int *ordinal, int32_t *chosen /*[IMP_CHUNK]*/,
+                                  int *dup_flag) {
     const size_t base = (size_t)r * G.Npad;
     const int tid = threadIdx.x;
     for (int first = 0; first < count; first += IMP_CHUNK) {
         const int m = min(IMP_CHUNK, count - first);
         __syncthreads();
-        if (tid < m * 10) {
-            const uint32_t ord = (uint32_t)(*ordinal + first + tid / 10), t = (uint32_t)(tid % 10);
-            u32x4 x = philox(c->seed, ord, (uint32_t)c->day, PU_IMPORT | (t << 8), 0);
-            float p = u01f(x.x);
-            int k = G.n_import_classes - 1;
-            for (int j = 0; j < G.n_import_classes; j++) if (p <= G.import_cum[j]) { k = j; break; }
-            int32_t s = G.age_start[G.import_lo[k]], en = G.age_start[G.import_hi[k] + 1];
-            int32_t pi = s + (int32_t)(x.y % (uint32_t)(en - s));
-            cand[tid] = H_STATE(G.hot[base + pi]) == RB_SUSCEPTIBLE ? pi : -1;
+        if (tid == 0) *dup_flag = 0;
+        int32_t pick = -1;
+        if (tid < m) {
+            for (uint32_t t = 0; t < 10 && pick < 0; t++) pick = import_draw(G, c, base, (uint32_t)(*ordinal + first + tid), t);
+            chosen[tid] = pick;
+            if (pick >= 0) atomicMin(&G.rec[base + pick].winner, (unsigned long long)tid);
         }
         __syncthreads();
-        if (tid == 0) {
+        if (pick >= 0 && G.rec[base + pick].winner != (unsigned long long)tid) *dup_flag = 1;
+        __syncthreads();
+        if (pick >= 0) G.rec[base + pick].winner = KEY_IDLE;
+        if (*dup_flag && tid == 0) {
             for (int j = 0; j < m; j++) {
                 int32_t found = -1;
-                for (int t = 0; t < 10 && found < 0; t++) {
-                    int32_t pi = cand[j * 10 + t];
+                for (uint32_t t = 0; t < 10 && found < 0; t++) {
+                    const int32_t pi = import_draw(G, c, base, (uint32_t)(*ordinal + first + j), t);
                     if (pi < 0) continue;
                     bool taken = false;
                     for (int q = 0; q < j; q++) if (chosen[q] == pi) { taken = true; break; }
@@ -502,7 +538,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
     __syncthreads();
     int ordinal = 0;       // uniform across the CTA
     for (int i = 0; i < dp->n_imports; i++)
-        import_infections(G, r, c, dp->import_amount[i], dp->import_variant[i], &ordinal, (int32_t *)sk, sv);
+        import_infections(G, r, c, dp->import_amount[i], dp->import_variant[i], &ordinal, sv, &sh_i[2]);
     __syncthreads();
     for (int i = tid; i < G.n_ages; i += blockDim.x) { c->counts[RB_A_NEW_INFECTIONS][i] = 0; c->counts[RB_A_DETECTED][i] = 0; }
     if (tid < RB_N_PLACES) c->daily_contacts[tid] = 0;
@@ -510,7 +546,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
     __syncthreads();
     if (tid == 0) { c->epoch = dp->table_epoch; c->total_infectors = 0; c->total_infections = 0; c->exposed_per_day = 0; }
     for (int v = 0; v < G.n_variants; v++)
-        if (dp->trickle[v]) import_infections(G, r, c, dp->trickle[v], v, &ordinal, (int32_t *)sk, sv);
+        if (dp->trickle[v]) import_infections(G, r, c, dp->trickle[v], v, &ordinal, sv, &sh_i[2]);
     __syncthreads();
 
     TS(1);   // imports + init_day
@@ -529,6 +565,12 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
             block_sort_pairs(qk, qa, nq, G.cap_queue, sk, sv);
     }
     __syncthreads();
+    if (c->drained) {      // k_resolve already marked the queued agents detected: book the counts here, where the reference drains
+        for (int age = tid; age < G.n_ages; age += blockDim.x) {
+            const int d = c->drain_det[age];
+            if (d) { c->counts[RB_A_DETECTED][age] += d; c->counts[RB_A_ALL_DETECTED][age] += d; c->drain_det[age] = 0; }
+        }
+    } else
     for (uint32_t i = tid; i < nq; i += blockDim.x) {
         int32_t a = qa[i];
         uint32_t h = G.hot[base + a];
@@ -538,6 +580,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
         count_add(c, RB_A_DETECTED, age, 1); count_add(c, RB_A_ALL_DETECTED, age, 1);
     }
     __syncthreads();
+    if (tid == 0) c->drained = 0u;
 
     TS(2);   // queue drain
     if (ct && nq > 0) {
@@ -898,15 +941,16 @@ __device__ __forceinline__ void stage_transition(const Eng &G, int r, RepCtr *c,
 __device__ __forceinline__ void stage_active(const Eng &G, int r, RepCtr *c, RepCtr *cd, WarpRings &W, uint32_t head, uint32_t m,
                                              uint32_t &e_tail, uint32_t &t_tail, int lane) {
     const size_t base = (size_t)r * G.Npad;
-    bool want_e = false, want_t = false;
+    bool want_e = false, want_t = false, removed = false;
+    int infected_others = 0;
     uint32_t a = 0, h = 0, desc = 0;
     if ((uint32_t)lane < m) {
         a = W.qi[(head + lane) & (SW_QCAP - 1)];
         h = G.hot[base + a];               // the only per-agent gather of the sweep: ~3 % of the agents on an average day
         const uint32_t st = H_STATE(h);
         if (st >= RB_RECOVERED) {          // R bookkeeping, main.pyx:1969-1972 (only agents not yet included reach here)
-            atomicAdd(&cd->total_infectors, 1);
-            atomicAdd(&cd->total_infections, (int)(G.rec[base + a].cold & 0xffffu));
+            removed = true;
+            infected_others = (int)(G.rec[base + a].cold & 0xffffu);
             G.hot[base + a] = h | H_INCL;
             atomicAnd(&G.act[(size_t)r * G.sus_words + (a >> 5)], ~(1u << (a & 31)));   // nothing left to do for this agent
         } else if (h & H_FRESH) {          // infected today before the sweep: wait until tomorrow, main.pyx:402-403
@@ -927,6 +971,12 @@ __device__ __forceinline__ void stage_active(const Eng &G, int r, RepCtr *c, Rep
             h = H_SET_DL(h, dl);
             if (dl == 0) want_t = true; else G.hot[base + a] = h;
         }
+    }
+    const uint32_t rm = __ballot_sync(0xffffffffu, removed);
+    if (rm) {                              // one pair of atomics per warp batch instead of one per removed agent
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) infected_others += __shfl_xor_sync(0xffffffffu, infected_others, o);
+        if (lane == 0) { atomicAdd(&cd->total_infectors, __popc(rm)); if (infected_others) atomicAdd(&cd->total_infections, infected_others); }
     }
     e_tail = ring_push(W.ea, W.ed, e_tail, want_e, a, desc, lane);
     t_tail = ring_push(W.ta, W.tw, t_tail, want_t, a, h, lane);
@@ -1048,32 +1098,46 @@ __global__ void __launch_bounds__(SW_THREADS, 4) k_sweep(Eng G) {
 
 __device__ __forceinline__ void expose_survivors(const Eng &G, int r, RepCtr *c, RepCtr *cd, const DevTable *tb, const uint2 *items, const uint32_t *sus,
                                                  Attempt *succ, uint32_t cap_succ, const uint32_t *ri, const uint32_t *rx, uint32_t head, uint32_t m, int lane) {
-    if ((uint32_t)lane >= m) return;
     const size_t base = (size_t)r * G.Npad;
-    const uint2 it = items[ri[(head + lane) & (EX_RCAP - 1)]];
-    const uint32_t info = rx[(head + lane) & (EX_RCAP - 1)];
-    const uint32_t slot = info & 127u, row = (info >> 7) & 127u, kq = info >> 14;
-    const uint32_t a = it.x, age = (it.y >> 7) & 127u, dayidx = (it.y >> 14) & 31u, var = (it.y >> 20) & 3u;
-    const rb_variant *v = &G.variants[var];
-    float si = v->iot[dayidx];
-    if ((it.y >> 19) & 1u) si = si * v->p_asymptomatic_infection;
-    const u32x4 y = philox(c->seed, a, (uint32_t)c->day, PU_CONTACT2 | (slot << 8), 0);
-    const uint32_t t = (uint32_t)tb->start[age][row] + y.x % (uint32_t)tb->size[age][row];
-    // person_expose (main.pyx:238-244): only a SUSCEPTIBLE target can be infected; the 1-bit-per-agent map keeps
-    // this random gather inside L2 instead of pulling a 32-byte DRAM sector per contact
-    if (!((__ldg(&sus[t >> 5]) >> (t & 31)) & 1u)) return;
-    const int tage = tb->susc_uniform[age][row] ? (int)tb->lo_age[age][row]
-                                                : age_in_band(G, (int32_t)t, tb->lo_age[age][row], tb->hi_age[age][row]);
-    const float pr = (si * v->tab[RB_T_SUSCEPTIBILITY][tage]) * v->infectiousness_multiplier;
-    if (!(((double)y.y * (1.0 / 4294967296.0)) * (double)kq < (double)pr * 256.0)) return;
-    const float mp = tb->mask_p[age][row];
-    if (mp != 0.0f) {
-        const float ma = mp * v->p_mask_protects_others, mb = mp * v->p_mask_protects_wearer;
-        const float pm = (ma + mb) - ma * mb;
-        if (chance((double)y.z * (1.0 / 4294967296.0), pm)) return;
+    bool ok = false;
+    uint32_t a = 0, t = 0, slot = 0;
+    if ((uint32_t)lane < m) {
+        const uint2 it = items[ri[(head + lane) & (EX_RCAP - 1)]];
+        const uint32_t info = rx[(head + lane) & (EX_RCAP - 1)];
+        const uint32_t row = (info >> 7) & 127u, kq = info >> 14;
+        slot = info & 127u;
+        a = it.x;
+        const uint32_t age = (it.y >> 7) & 127u, dayidx = (it.y >> 14) & 31u, var = (it.y >> 20) & 3u;
+        const rb_variant *v = &G.variants[var];
+        float si = v->iot[dayidx];
+        if ((it.y >> 19) & 1u) si = si * v->p_asymptomatic_infection;
+        const u32x4 y = philox(c->seed, a, (uint32_t)c->day, PU_CONTACT2 | (slot << 8), 0);
+        t = (uint32_t)tb->start[age][row] + y.x % (uint32_t)tb->size[age][row];
+        // person_expose (main.pyx:238-244): only a SUSCEPTIBLE target can be infected; the 1-bit-per-agent map keeps
+        // this random gather inside L2 instead of pulling a 32-byte DRAM sector per contact
+        if ((__ldg(&sus[t >> 5]) >> (t & 31)) & 1u) {
+            const int tage = tb->susc_uniform[age][row] ? (int)tb->lo_age[age][row]
+                                                        : age_in_band(G, (int32_t)t, tb->lo_age[age][row], tb->hi_age[age][row]);
+            const float pr = (si * v->tab[RB_T_SUSCEPTIBILITY][tage]) * v->infectiousness_multiplier;
+            if (((double)y.y * (1.0 / 4294967296.0)) * (double)kq < (double)pr * 256.0) {
+                ok = true;
+                const float mp = tb->mask_p[age][row];
+                if (mp != 0.0f) {
+                    const float ma = mp * v->p_mask_protects_others, mb = mp * v->p_mask_protects_wearer;
+                    const float pm = (ma + mb) - ma * mb;
+                    if (chance((double)y.z * (1.0 / 4294967296.0), pm)) ok = false;
+                }
+            }
+        }
     }
+    const uint32_t okm = __ballot_sync(0xffffffffu, ok);
+    if (!okm) return;
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(&cd->n_succ, (uint32_t)__popc(okm));     // one atomic per warp batch
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (!ok) return;
+    const uint32_t idx = b + __popc(okm & ((1u << lane) - 1u));
     const unsigned long long key = ((unsigned long long)sweep_pos(G, c, a) << 7) | slot;
-    const uint32_t idx = atomicAdd(&cd->n_succ, 1u);
     if (idx < cap_succ) {
         succ[idx].cand = t; succ[idx].parent = a; succ[idx].key = key;
         if (!G.xbuf) atomicMin(&G.rec[base + t].winner, key);     // sharded: k_merge does it over every rank's list
@@ -1219,6 +1283,11 @@ __global__ void __launch_bounds__(256) k_merge(Eng G) {
 }
 
 // ---------------------------------------------------------------- k_resolve
+// DRAIN: this day is followed by the fused day boundary, so tomorrow's test queue -- complete once today's sweep is
+// over -- is drained here by the whole grid instead of by tomorrow's single boundary CTA (HealthcareSystem.iterate,
+// main.pyx:514-545: every queued agent is detected).  The per-age detection counts are parked in drain_det and booked
+// by the boundary at the point where the reference drains, so every stats row is unchanged.
+template <bool DRAIN>
 __global__ void __launch_bounds__(256) k_resolve(Eng G) {
     const int r = blockIdx.y;
     RepCtr *c = &G.ctr[r];
@@ -1232,6 +1301,18 @@ __global__ void __launch_bounds__(256) k_resolve(Eng G) {
         if (w != at.key) continue;                             // first infector in sweep order wins
         device_infect(G, r, c, (int32_t)at.cand, (int32_t)at.parent, src_h, 0, (int)(at.key & 127ull), false);
         G.rec[base + at.cand].winner = KEY_IDLE;
+    }
+    if (DRAIN) {
+        const uint32_t nq = min(c->n_newq, G.cap_queue);
+        const int32_t *qa = G.q_agent + ((size_t)r * 2 + (c->qsel ^ 1u)) * G.cap_queue;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+            const int32_t a = qa[i];
+            const uint32_t h = G.hot[base + a];
+            if (h & H_DET) set_problem(c, RB_WRONG_STATE);   // person_detect, main.pyx:294-298
+            G.hot[base + a] = (h & ~H_QUEUED) | H_DET;
+            atomicAdd(&c->drain_det[age_of(G, a)], 1);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) c->drained = 1u;
     }
 }
 
@@ -1607,7 +1688,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     e->list_blocks = (sms * 4 + R - 1) / R; if (e->list_blocks < 2) e->list_blocks = 2;
     // k_resolve is a chain of dependent scattered accesses per infection: enough threads for one pass over the day's list
     e->resolve_blocks = (int)((G.N / 128 + 255) / 256); if (e->resolve_blocks < e->list_blocks) e->resolve_blocks = e->list_blocks;
-    if (e->resolve_blocks > 64) e->resolve_blocks = 64;
+    { int cap = sms * 16 / R; if (cap < 64) cap = 64; if (e->resolve_blocks > cap) e->resolve_blocks = cap; }
     k_init<<<dim3(e->sweep_blocks, R), 256, 0, e->stream>>>(G); e->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
@@ -1686,7 +1767,7 @@ static void launch_segment(rb_engine *e, cudaStream_t st) {
     const Eng &G = e->G;
     k_sweep<<<dim3(e->sweep_blocks, G.R), SW_THREADS, 0, st>>>(G);
     k_expose<<<dim3(e->list_blocks, G.R), EX_THREADS, 0, st>>>(G);
-    k_resolve<<<dim3(e->resolve_blocks, G.R), 256, 0, st>>>(G);
+    k_resolve<true><<<dim3(e->resolve_blocks, G.R), 256, 0, st>>>(G);
     k_between<<<G.R, PRE_THREADS, 0, st>>>(G);
 }
 
@@ -1757,8 +1838,8 @@ static int launch_day_sharded(rb_engine *e, bool last) {
     k_expose<<<dim3(e->list_blocks, 1), EX_THREADS, 0, st>>>(G);
     NK(g_nccl.AllGather(G.xbuf + (size_t)G.rank * G.xslot, G.xbuf, G.xslot, ncclChar, e->comm, st));
     k_merge<<<e->merge_blocks, 256, 0, st>>>(G);
-    k_resolve<<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G);
-    if (last) k_post<<<1, PRE_THREADS, 0, st>>>(G); else k_between<<<1, PRE_THREADS, 0, st>>>(G);
+    if (last) { k_resolve<false><<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G); k_post<<<1, PRE_THREADS, 0, st>>>(G); }
+    else { k_resolve<true><<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G); k_between<<<1, PRE_THREADS, 0, st>>>(G); }
     e->launches += 5;
     return 0;
 }
@@ -1790,7 +1871,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     while (mid > 0) { CK(cudaGraphLaunch(e->graph[1], e->stream)); mid -= 1; e->launches += 4; }
     k_sweep<<<dim3(e->sweep_blocks, R), SW_THREADS, 0, e->stream>>>(G);
     k_expose<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G);
-    k_resolve<<<dim3(e->resolve_blocks, R), 256, 0, e->stream>>>(G);
+    k_resolve<false><<<dim3(e->resolve_blocks, R), 256, 0, e->stream>>>(G);
     k_post<<<R, PRE_THREADS, 0, e->stream>>>(G);
     e->launches += 4;
     CK(cudaEventRecord(e->ev1, e->stream));
@@ -1813,7 +1894,7 @@ extern "C" int rb_step_profiled(rb_engine *e, int32_t n_days, float *ms_per_kern
         k_pre<<<R, PRE_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[1], e->stream));
         k_sweep<<<dim3(e->sweep_blocks, R), SW_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[2], e->stream));
         k_expose<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G); CK(cudaEventRecord(v[3], e->stream));
-        k_resolve<<<dim3(e->resolve_blocks, R), 256, 0, e->stream>>>(G); CK(cudaEventRecord(v[4], e->stream));
+        k_resolve<false><<<dim3(e->resolve_blocks, R), 256, 0, e->stream>>>(G); CK(cudaEventRecord(v[4], e->stream));
         k_post<<<R, PRE_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[5], e->stream));
         e->launches += 5;
     }

@@ -1,0 +1,52 @@
+"""Population-sharded runs (BASELINE configs[4]): one process per GPU, every rank builds the same Context and joins
+the others through `shard=(rank, nranks, unique_id)`; the engine exchanges the day's cross-shard events with one NCCL
+all-gather per simulated day (include/reina_b200.h, rb_shard_init).
+
+`torch.distributed` is used only to hand rank 0's NCCL unique id to the other ranks (any backend, gloo works on CPU).
+"""
+import os
+
+from . import _abi
+
+
+def world():
+    """(rank, world_size, local_rank) from the torchrun environment; (0, 1, 0) when not launched by torchrun."""
+    return (int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')),
+            int(os.environ.get('LOCAL_RANK', '0')))
+
+
+def exchange_unique_id(make_id=None, dist=None):
+    """Rank 0 creates the 128-byte NCCL unique id, every rank returns it.  `dist` is an initialised
+    torch.distributed module (or None for a single process); `make_id` defaults to the CUDA library's
+    rb_shard_unique_id and is injectable so that the plumbing can be tested on CPU."""
+    make_id = make_id or _abi.shard_unique_id
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return make_id()
+    box = [make_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    uid = box[0]
+    if not isinstance(uid, (bytes, bytearray)) or len(uid) != 128:
+        raise _abi.EngineError('unique id broadcast failed')
+    return bytes(uid)
+
+
+def shard_spec(dist=None, exchange_capacity=0.0, make_id=None):
+    """The `shard=` argument of model.Context for this process."""
+    if dist is not None and dist.is_initialized():
+        rank, n = dist.get_rank(), dist.get_world_size()
+    else:
+        rank, n = 0, 1
+    return (rank, n, exchange_unique_id(make_id, dist), exchange_capacity)
+
+
+def merge_agents(per_rank_agents):
+    """Canonical agent records of the whole population from every rank's rb_read_agents: agent a is taken from the
+    rank that owns it (day counters and severity are authoritative there)."""
+    import numpy as np
+    n = len(per_rank_agents)
+    out = per_rank_agents[0].copy()
+    owner = _abi.owner_of(np.arange(len(out)), n)
+    for r in range(1, n):
+        sel = owner == r
+        out[sel] = per_rank_agents[r][sel]
+    return out
