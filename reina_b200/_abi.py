@@ -79,7 +79,8 @@ AGENT_DTYPE = np.dtype([
 assert AGENT_DTYPE.itemsize == 20, AGENT_DTYPE.itemsize
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-CUDA_LIB_PATH = os.path.join(_HERE, 'libreina_b200.so')
+# REINA_B200_LIB: measurement aid (tools/variants.sh builds the library with different tuning macros)
+CUDA_LIB_PATH = os.environ.get('REINA_B200_LIB') or os.path.join(_HERE, 'libreina_b200.so')
 
 SYMBOLS = ['create', 'destroy', 'reset', 'step_profiled', 'set_contact_table', 'set_schedule', 'step', 'sync', 'day',
            'snapshot', 'row_len', 'read_stats', 'read_moments', 'read_per_age', 'problem', 'sample', 'read_agents',

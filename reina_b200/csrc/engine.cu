@@ -744,14 +744,22 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
 //                               work items allocated with a warp prefix sum + one atomic and written coalesced
 //   ring T (state changes)   -> stage T: symptom onset (gamma draw, durations, testing queue), end of illness,
 //                               ward / ICU exits (capacity events tagged with the agent's sweep position)
-#define SW_THREADS 256
+#ifndef SW_THREADS
+#define SW_THREADS 128
+#endif
 #define SW_WARPS (SW_THREADS / 32)
 #define SW_CHUNK 256
-#define SW_QCAP 512
+#define SW_QCAP 256          // ring A takes at most 128 entries per step on top of < 32 left over
 #define SW_RCAP 64
+#ifndef SW_PFD
+#define SW_PFD 3             // packed-word chunks in flight per warp (cp.async), 1 KB each; 0 = plain loads
+#endif
+#ifndef SW_CTAS_PER_SM
+#define SW_CTAS_PER_SM 8
+#endif
 
 struct WarpRings {
-    uint32_t qi[SW_QCAP];                   // ring A: agent index
+    uint32_t qi[SW_QCAP], qw[SW_QCAP];      // ring A: agent index, packed word as streamed (dense days)
     uint32_t ea[SW_RCAP], ed[SW_RCAP];      // ring E: agent index, contact descriptor
     uint32_t ta[SW_RCAP], tw[SW_RCAP];      // ring T: agent index, packed word (day counters already advanced)
 };
@@ -937,153 +945,217 @@ __device__ __forceinline__ void stage_transition(const Eng &G, int r, RepCtr *c,
     }
 }
 
-// stage 1 over one batch of ring A; pushes to rings E and T
-__device__ __forceinline__ void stage_active(const Eng &G, int r, RepCtr *c, RepCtr *cd, WarpRings &W, uint32_t head, uint32_t m,
-                                             uint32_t &e_tail, uint32_t &t_tail, int lane) {
-    const size_t base = (size_t)r * G.Npad;
-    bool want_e = false, want_t = false, removed = false;
-    int infected_others = 0;
-    uint32_t a = 0, h = 0, desc = 0;
-    if ((uint32_t)lane < m) {
-        a = W.qi[(head + lane) & (SW_QCAP - 1)];
-        h = G.hot[base + a];               // the only per-agent gather of the sweep: ~3 % of the agents on an average day
-        const uint32_t st = H_STATE(h);
-        if (st >= RB_RECOVERED) {          // R bookkeeping, main.pyx:1969-1972 (only agents not yet included reach here)
-            removed = true;
-            infected_others = (int)(G.rec[base + a].cold & 0xffffu);
-            G.hot[base + a] = h | H_INCL;
-            atomicAnd(&G.act[(size_t)r * G.sus_words + (a >> 5)], ~(1u << (a & 31)));   // nothing left to do for this agent
-        } else if (h & H_FRESH) {          // infected today before the sweep: wait until tomorrow, main.pyx:402-403
-            G.hot[base + a] = h & ~H_FRESH;
-        } else {
-            const uint32_t sev = H_SEV(h), var = H_VAR(h);
-            uint32_t dl = H_DL(h);
-            if (st == RB_INCUBATION || st == RB_ILLNESS) {
-                const int dayidx = st == RB_INCUBATION ? -(int)dl : (int)H_DOI(h);
-                if (!(h & H_DET) && dayidx >= -10 && dayidx <= 10 && G.variants[var].iot[dayidx + 10] != 0.0f) {
-                    want_e = true;
-                    const uint32_t cls = (st == RB_ILLNESS && sev != RB_ASYMPTOMATIC) ? 1u : 0u;   // factor 0.5, limit 5
-                    desc = ((uint32_t)(dayidx + 10) << 14) | ((sev == RB_ASYMPTOMATIC ? 1u : 0u) << 19) | (var << 20) | (cls << 22);
-                }
-                if (st == RB_ILLNESS) { uint32_t doi = H_DOI(h); if (doi < 31) doi++; h = H_SET_DOI(h, doi); }
+// stage 1 for one active agent: R bookkeeping, "infected today" flag, day counters, what happens next
+__device__ __forceinline__ void stage_active_lane(const Eng &G, int r, RepCtr *c, size_t base, uint32_t a, uint32_t &h, bool &want_e, bool &want_t,
+                                                  bool &removed, int &infected_others, uint32_t &desc) {
+    const uint32_t st = H_STATE(h);
+    if (st >= RB_RECOVERED) {          // R bookkeeping, main.pyx:1969-1972 (only agents not yet included reach here)
+        removed = true;
+        infected_others = (int)(G.rec[base + a].cold & 0xffffu);
+        G.hot[base + a] = h | H_INCL;
+        atomicAnd(&G.act[(size_t)r * G.sus_words + (a >> 5)], ~(1u << (a & 31)));   // nothing left to do for this agent
+    } else if (h & H_FRESH) {          // infected today before the sweep: wait until tomorrow, main.pyx:402-403
+        G.hot[base + a] = h & ~H_FRESH;
+    } else {
+        const uint32_t sev = H_SEV(h), var = H_VAR(h);
+        uint32_t dl = H_DL(h);
+        if (st == RB_INCUBATION || st == RB_ILLNESS) {
+            const int dayidx = st == RB_INCUBATION ? -(int)dl : (int)H_DOI(h);
+            if (!(h & H_DET) && dayidx >= -10 && dayidx <= 10 && G.variants[var].iot[dayidx + 10] != 0.0f) {
+                want_e = true;
+                const uint32_t cls = (st == RB_ILLNESS && sev != RB_ASYMPTOMATIC) ? 1u : 0u;   // factor 0.5, limit 5
+                desc = ((uint32_t)(dayidx + 10) << 14) | ((sev == RB_ASYMPTOMATIC ? 1u : 0u) << 19) | (var << 20) | (cls << 22);
             }
-            if (dl > 0) dl--;
-            h = H_SET_DL(h, dl);
-            if (dl == 0) want_t = true; else G.hot[base + a] = h;
+            if (st == RB_ILLNESS) { uint32_t doi = H_DOI(h); if (doi < 31) doi++; h = H_SET_DOI(h, doi); }
         }
+        if (dl > 0) dl--;
+        h = H_SET_DL(h, dl);
+        if (dl == 0) want_t = true; else G.hot[base + a] = h;
     }
-    const uint32_t rm = __ballot_sync(0xffffffffu, removed);
-    if (rm) {                              // one pair of atomics per warp batch instead of one per removed agent
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) infected_others += __shfl_xor_sync(0xffffffffu, infected_others, o);
-        if (lane == 0) { atomicAdd(&cd->total_infectors, __popc(rm)); if (infected_others) atomicAdd(&cd->total_infections, infected_others); }
-    }
-    e_tail = ring_push(W.ea, W.ed, e_tail, want_e, a, desc, lane);
-    t_tail = ring_push(W.ta, W.tw, t_tail, want_t, a, h, lane);
 }
 
-__global__ void __launch_bounds__(SW_THREADS, 4) k_sweep(Eng G) {
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int nbytes = valid ? 16 : 0;      // src-size 0: nothing is read, the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// the four packed words of one lane -> ring A (index and word); returns the new tail
+__device__ __forceinline__ uint32_t sweep_push4(WarpRings &W, uint32_t tail, const uint4 w, uint32_t a_first, int lane) {
+    const uint32_t hw[4] = {w.x, w.y, w.z, w.w};
+    uint32_t act = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t st = H_STATE(hw[j]);
+        if (st != RB_SUSCEPTIBLE && !(st >= RB_RECOVERED && (hw[j] & H_INCL))) act |= 1u << j;
+    }
+    if (!__any_sync(0xffffffffu, act != 0)) return tail;
+    const uint32_t mine = __popc(act);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t p = tail + incl - mine;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (act & (1u << j)) { W.qi[p & (SW_QCAP - 1)] = a_first + j; W.qw[p & (SW_QCAP - 1)] = hw[j]; p++; }
+    return tail + tot;
+}
+
+// The kernel is one producer / consumer loop per warp.  The producer fills ring A from today's source -- the packed
+// words themselves on dense days, the activity bitmap on sparse days -- until a full batch of 32 is queued; the
+// consumer runs each stage on one batch.  Every stage is instantiated exactly ONCE: the stages are thousands of
+// instructions each, and a second inlined copy in the hot loop pushes it out of the instruction cache.
+__global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
     __shared__ WarpRings s_rings[SW_WARPS];
+#if SW_PFD > 0
+    __shared__ uint4 s_pf[SW_WARPS][SW_PFD][2][32];
+#endif
     const int r = blockIdx.y;
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
     const DevTable *tb = G.tables[c->epoch];
-    const uint4 *act4 = reinterpret_cast<const uint4 *>(G.act + (size_t)r * G.sus_words);
     uint2 *items = G.items + (size_t)r * G.cap_items;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpRings &W = s_rings[warp];
     RepCtr *cd = !G.xbuf ? c : xslot_of(G, G.rank).hdr;      // counters the sweep adds to
-    // One bit per agent says whether the sweep has anything to do for it (infected, or removed and not yet counted in
-    // R), so the pass over all N agents reads 1/32 of the packed state -- an L2-resident bitmap -- and only the
-    // active agents' words are gathered.  A warp step covers 32 lanes x 128 agents = one ownership stripe.
-    const int n_vec = G.sus_words >> 2;
     const int nrk = G.nranks, rk = G.rank;
+    const int stride = gridDim.x * SW_WARPS;
+    const bool stream = c->stream_mode != 0;
     uint32_t head = 0, tail = 0, e_head = 0, e_tail = 0, t_head = 0, t_tail = 0;
-    if (c->stream_mode) {
-        // dense day: coalesced 16-byte loads of the packed words themselves, 256 agents per warp step; the queued
-        // agents' words are re-read in stage 1 from L1
-        const uint4 *hot4 = reinterpret_cast<const uint4 *>(G.hot + base);
-        const int n_chunks = (G.Npad + SW_CHUNK - 1) / SW_CHUNK, n4 = G.Npad >> 2;
-        const int n_mine = (((n_chunks + 15) >> 4) + nrk - 1) / nrk * 16;      // this rank's chunks: 16 per stripe
-        for (int j = blockIdx.x * SW_WARPS + warp; j < n_mine; j += gridDim.x * SW_WARPS) {
-            const int chunk = nrk == 1 ? j : ((((j >> 4) * nrk + rk) << 4) | (j & 15));
-            if (chunk >= n_chunks) continue;
-            const int a0 = chunk * SW_CHUNK;
-            const int i0 = (a0 >> 2) + lane, i1 = i0 + 32;
-            uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
-            if (i0 < n4) w0 = hot4[i0];
-            if (i1 < n4) w1 = hot4[i1];
-            const uint32_t hw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-            uint32_t act = 0;
+
+    // ---- producer state.  Dense day: the packed words are streamed, 256 agents (1 KB) per warp step, in two halves of
+    // 128 so that ring A never takes more than 128 entries at once.  Sparse day: one bit per agent says whether the
+    // sweep has anything to do for it (infected, or removed and not yet counted in R), so the pass over all N agents
+    // reads 1/32 of the packed state -- an L2-resident bitmap -- and only the active agents' words are gathered; a
+    // warp step covers 32 lanes x 128 agents = one ownership stripe.
+    const uint4 *hot4 = reinterpret_cast<const uint4 *>(G.hot + base);
+    const uint4 *act4 = reinterpret_cast<const uint4 *>(G.act + (size_t)r * G.sus_words);
+    const int n_chunks = (G.Npad + SW_CHUNK - 1) / SW_CHUNK, n4 = G.Npad >> 2, n_vec = G.sus_words >> 2;
+    const int n_mine = stream ? (((n_chunks + 15) >> 4) + nrk - 1) / nrk * 16        // this rank's chunks: 16 per stripe
+                              : (((n_vec + 31) >> 5) + nrk - 1) / nrk;              // this rank's bitmap steps
+    int j = blockIdx.x * SW_WARPS + warp;
+    bool more = j < n_mine;
+    uint4 wb = make_uint4(0, 0, 0, 0);      // dense: second half of the current chunk; sparse: this lane's 128 activity bits
+    uint32_t cw = 0, a0 = 0;
+    int part = 0;                           // dense: 0 = load a chunk, 1 = second half pending; sparse: word of `wb` in `cw` (4 = none)
+    if (!stream) part = 4;
+#if SW_PFD > 0
+    uint4 (*pf)[2][32] = s_pf[warp];
+    int slot = 0;
+    auto chunk_of = [&](int jj) { return nrk == 1 ? jj : ((((jj >> 4) * nrk + rk) << 4) | (jj & 15)); };
+    auto fetch = [&](int jj, int sl) {      // each lane copies its two 16-byte pieces of chunk jj into its own slots
+        const int chunk = chunk_of(jj);
+        const int i0 = chunk * (SW_CHUNK / 4) + lane, i1 = i0 + 32;
+        const bool in = jj < n_mine && chunk < n_chunks;
+        const bool v0 = in && i0 < n4, v1 = in && i1 < n4;
+        cp_async16(&pf[sl][0][lane], hot4 + (v0 ? i0 : 0), v0);
+        cp_async16(&pf[sl][1][lane], hot4 + (v1 ? i1 : 0), v1);
+        cp_async_commit();
+    };
+    if (stream) {
 #pragma unroll
-            for (int j2 = 0; j2 < 8; j2++) {
-                uint32_t st = H_STATE(hw[j2]);
-                if (st != RB_SUSCEPTIBLE && !(st >= RB_RECOVERED && (hw[j2] & H_INCL))) act |= 1u << j2;
+        for (int d = 0; d < SW_PFD; d++) fetch(j + d * stride, d);
+    }
+#else
+    auto chunk_of = [&](int jj) { return nrk == 1 ? jj : ((((jj >> 4) * nrk + rk) << 4) | (jj & 15)); };
+#endif
+
+    for (;;) {
+        // ---------------- produce
+        while (more && tail - head < 32) {
+            if (stream) {
+                if (part == 0) {
+                    const int chunk = chunk_of(j);
+                    uint4 w0 = make_uint4(0, 0, 0, 0);
+#if SW_PFD > 0
+                    cp_async_wait<SW_PFD - 1>();
+                    w0 = pf[slot][0][lane]; wb = pf[slot][1][lane];
+                    fetch(j + SW_PFD * stride, slot);          // refill the slot just read
+                    slot = slot + 1 == SW_PFD ? 0 : slot + 1;
+#else
+                    const int i0 = chunk * (SW_CHUNK / 4) + lane, i1 = i0 + 32;
+                    wb = w0;
+                    if (chunk < n_chunks && i0 < n4) w0 = hot4[i0];
+                    if (chunk < n_chunks && i1 < n4) wb = hot4[i1];
+#endif
+                    a0 = (uint32_t)chunk * SW_CHUNK;
+                    tail = sweep_push4(W, tail, w0, a0 + lane * 4, lane);
+                    part = 1;
+                } else {
+                    tail = sweep_push4(W, tail, wb, a0 + 128 + lane * 4, lane);
+                    part = 0;
+                    j += stride; more = j < n_mine;
+                }
+            } else {
+                if (part == 4) {                               // next 32 x 128 activity bits
+                    const int v0 = (nrk == 1 ? j : j * nrk + rk) * 32;
+                    j += stride;
+                    const int vi = v0 + lane;
+                    wb = make_uint4(0, 0, 0, 0);
+                    if (vi < n_vec) wb = __ldg(&act4[vi]);
+                    a0 = (uint32_t)vi * 128u;
+                    if (__any_sync(0xffffffffu, (wb.x | wb.y | wb.z | wb.w) != 0u)) { part = 0; cw = wb.x; }
+                    else more = j < n_mine;
+                } else if (!__any_sync(0xffffffffu, cw != 0u)) {
+                    part++;
+                    cw = part == 1 ? wb.y : (part == 2 ? wb.z : wb.w);
+                    if (part == 4) more = j < n_mine;
+                } else {
+                    // every lane queues up to 4 of its set bits per round: at most 128 pushes, the ring holds 256
+                    const uint32_t mine = min(__popc(cw), 4);
+                    uint32_t incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                    uint32_t p = tail + incl - mine;
+                    for (uint32_t k = 0; k < mine; k++) {
+                        W.qi[p & (SW_QCAP - 1)] = a0 + (uint32_t)part * 32u + (uint32_t)(__ffs(cw) - 1);
+                        cw &= cw - 1u;
+                        p++;
+                    }
+                    tail += tot;
+                }
             }
-            if (!__any_sync(0xffffffffu, act != 0)) continue;
-            uint32_t mine = __popc(act), incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-            uint32_t p = tail + incl - mine;
-#pragma unroll
-            for (int j2 = 0; j2 < 8; j2++)
-                if (act & (1u << j2)) { W.qi[p & (SW_QCAP - 1)] = (uint32_t)(a0 + (j2 < 4 ? lane * 4 + j2 : 128 + lane * 4 + (j2 - 4))); p++; }
-            tail += tot;
             __syncwarp();
-            while (tail - head >= 32) {
-                stage_active(G, r, c, cd, W, head, 32, e_tail, t_tail, lane); head += 32;
-                __syncwarp();
-                if (e_tail - e_head >= 32) { stage_expose(G, c, cd, tb, W, e_head, 32, items, lane); e_head += 32; }
-                if (t_tail - t_head >= 32) { stage_transition(G, r, c, W, t_head, 32, lane); t_head += 32; }
-                __syncwarp();
-            }
         }
-    } else {
-    const int n_steps = (n_vec + 31) >> 5, n_mine = (n_steps + nrk - 1) / nrk;
-    for (int j = blockIdx.x * SW_WARPS + warp; j < n_mine; j += gridDim.x * SW_WARPS) {
-        const int v0 = (nrk == 1 ? j : j * nrk + rk) * 32;
-        if (v0 >= n_vec) continue;
-        const int vi = v0 + lane;
-        uint4 bits = make_uint4(0, 0, 0, 0);
-        if (vi < n_vec) bits = __ldg(&act4[vi]);
-        if (!__any_sync(0xffffffffu, (bits.x | bits.y | bits.z | bits.w) != 0u)) continue;
-        uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            uint32_t w = bw[q];
-            const uint32_t abase = (uint32_t)vi * 128u + (uint32_t)q * 32u;
-            while (__any_sync(0xffffffffu, w != 0u)) {
-                // every lane queues up to 8 of its set bits per round: at most 256 pushes, the ring holds 512
-                uint32_t mine = min(__popc(w), 8), incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-                uint32_t p = tail + incl - mine;
-                for (uint32_t k = 0; k < mine; k++) {
-                    W.qi[p & (SW_QCAP - 1)] = abase + (uint32_t)(__ffs(w) - 1);
-                    w &= w - 1u;
-                    p++;
-                }
-                tail += tot;
-                __syncwarp();
-                while (tail - head >= 32) {
-                    if (G.dbg == 3) { head += 32; continue; }
-                    stage_active(G, r, c, cd, W, head, 32, e_tail, t_tail, lane); head += 32;
-                    __syncwarp();
-                    if (e_tail - e_head >= 32) { if (G.dbg != 1) stage_expose(G, c, cd, tb, W, e_head, 32, items, lane); e_head += 32; }
-                    if (t_tail - t_head >= 32) { if (G.dbg != 2) stage_transition(G, r, c, W, t_head, 32, lane); t_head += 32; }
-                    __syncwarp();
-                }
+        // ---------------- consume: full batches while the source lasts, whatever is left afterwards
+        const uint32_t av = tail - head;
+        if (av) {
+            const uint32_t m = min(32u, av);
+            const size_t gb = base;
+            bool want_e = false, want_t = false, removed = false;
+            int infected_others = 0;
+            uint32_t a = 0, h = 0, desc = 0;
+            if ((uint32_t)lane < m) {
+                a = W.qi[(head + lane) & (SW_QCAP - 1)];
+                // sparse days: the only per-agent gather of the sweep (~3 % of the agents); dense days: the word came with the stream
+                h = stream ? W.qw[(head + lane) & (SW_QCAP - 1)] : G.hot[gb + a];
+                stage_active_lane(G, r, c, gb, a, h, want_e, want_t, removed, infected_others, desc);
             }
+            head += m;
+            const uint32_t rm = __ballot_sync(0xffffffffu, removed);
+            if (rm) {                              // one pair of atomics per warp batch instead of one per removed agent
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) infected_others += __shfl_xor_sync(0xffffffffu, infected_others, o);
+                if (lane == 0) { atomicAdd(&cd->total_infectors, __popc(rm)); if (infected_others) atomicAdd(&cd->total_infections, infected_others); }
+            }
+            e_tail = ring_push(W.ea, W.ed, e_tail, want_e, a, desc, lane);
+            t_tail = ring_push(W.ta, W.tw, t_tail, want_t, a, h, lane);
+            __syncwarp();
         }
+        const bool flush = !more && tail == head;
+        const uint32_t e_av = e_tail - e_head, t_av = t_tail - t_head;
+        if (e_av >= 32 || (flush && e_av)) { const uint32_t m = min(32u, e_av); stage_expose(G, c, cd, tb, W, e_head, m, items, lane); e_head += m; }
+        if (t_av >= 32 || (flush && t_av)) { const uint32_t m = min(32u, t_av); stage_transition(G, r, c, W, t_head, m, lane); t_head += m; }
+        __syncwarp();
+        if (flush && e_tail == e_head && t_tail == t_head) break;
     }
-    }
-    // drain: whatever is left in ring A, then rings E and T (at most two partial batches each)
-    if (tail != head) { stage_active(G, r, c, cd, W, head, tail - head, e_tail, t_tail, lane); }
-    __syncwarp();
-    while (e_tail != e_head) { uint32_t m = min(32u, e_tail - e_head); stage_expose(G, c, cd, tb, W, e_head, m, items, lane); e_head += m; }
-    while (t_tail != t_head) { uint32_t m = min(32u, t_tail - t_head); stage_transition(G, r, c, W, t_head, m, lane); t_head += m; }
+#if SW_PFD > 0
+    cp_async_wait<0>();
+#endif
 }
 
 // ---------------------------------------------------------------- k_expose
@@ -1682,9 +1754,12 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     // launch geometry: grid-stride kernels sized in multiples of the SM count
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     int sms = prop.multiProcessorCount;
+    // the sweep fills the GPU exactly once: SW_CTAS_PER_SM resident CTAs per SM, shared out over the replicas (a grid a
+    // little larger than one wave would run its tail on a nearly empty GPU)
     int want = (G.sus_words / 4 + SW_WARPS * 32 - 1) / (SW_WARPS * 32);
-    int per_rep = (sms * 8 + R - 1) / R; if (per_rep < 4) per_rep = 4;
+    int per_rep = sms * SW_CTAS_PER_SM / R; if (per_rep < 1) per_rep = 1;
     e->sweep_blocks = want < per_rep ? want : per_rep; if (e->sweep_blocks < 1) e->sweep_blocks = 1;
+    CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 8 x 24 KB per SM
     e->list_blocks = (sms * 4 + R - 1) / R; if (e->list_blocks < 2) e->list_blocks = 2;
     // k_resolve is a chain of dependent scattered accesses per infection: enough threads for one pass over the day's list
     e->resolve_blocks = (int)((G.N / 128 + 255) / 256); if (e->resolve_blocks < e->list_blocks) e->resolve_blocks = e->list_blocks;
