@@ -68,6 +68,7 @@ struct DevTable {
     float nr_contacts[RB_MAX_AGES];
     double ncdf[RB_MAX_AGES][2][RB_NCDF];
     double cum_p[RB_MAX_AGES][RB_MAX_ROWS];
+    uint32_t cum24[RB_MAX_AGES][RB_MAX_ROWS];         // ceil(cum_p * 2^24): for a 24-bit uniform k / 2^24, (k / 2^24 < cum_p) == (k < cum24)
     int32_t start[RB_MAX_AGES][RB_MAX_ROWS];
     int32_t size[RB_MAX_AGES][RB_MAX_ROWS];
     float mask_p[RB_MAX_AGES][RB_MAX_ROWS];
@@ -983,14 +984,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // the four packed words of one lane -> ring A (index and word); returns the new tail
-__device__ __forceinline__ uint32_t sweep_push4(WarpRings &W, uint32_t tail, const uint4 w, uint32_t a_first, int lane) {
+__device__ __forceinline__ uint32_t sweep_push4(WarpRings &W, uint32_t tail, const uint4 w, uint32_t act, uint32_t a_first, int lane) {
     const uint32_t hw[4] = {w.x, w.y, w.z, w.w};
-    uint32_t act = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t st = H_STATE(hw[j]);
-        if (st != RB_SUSCEPTIBLE && !(st >= RB_RECOVERED && (hw[j] & H_INCL))) act |= 1u << j;
-    }
     if (!__any_sync(0xffffffffu, act != 0)) return tail;
     const uint32_t mine = __popc(act);
     uint32_t incl = mine;
@@ -1039,7 +1034,7 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
     int j = blockIdx.x * SW_WARPS + warp;
     bool more = j < n_mine;
     uint4 wb = make_uint4(0, 0, 0, 0);      // dense: second half of the current chunk; sparse: this lane's 128 activity bits
-    uint32_t cw = 0, a0 = 0;
+    uint32_t cw = 0, a0 = 0, abits = 0;
     int part = 0;                           // dense: 0 = load a chunk, 1 = second half pending; sparse: word of `wb` in `cw` (4 = none)
     if (!stream) part = 4;
 #if SW_PFD > 0
@@ -1082,10 +1077,16 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
                     if (chunk < n_chunks && i1 < n4) wb = hot4[i1];
 #endif
                     a0 = (uint32_t)chunk * SW_CHUNK;
-                    tail = sweep_push4(W, tail, w0, a0 + lane * 4, lane);
+                    // who is active comes from the bitmap (2 words per lane out of the chunk's 8, one 32-byte sector per
+                    // warp) rather than from decoding all eight packed words: this lane's agents are two nibbles
+                    const uint32_t *aw = G.act + (size_t)r * G.sus_words + (a0 >> 5) + (lane >> 3);
+                    uint32_t b0 = 0, b1 = 0;
+                    if (chunk < n_chunks) { b0 = __ldg(aw); b1 = __ldg(aw + 4); }
+                    b0 = (b0 >> ((lane & 7) * 4)) & 15u; abits = (b1 >> ((lane & 7) * 4)) & 15u;
+                    tail = sweep_push4(W, tail, w0, b0, a0 + lane * 4, lane);
                     part = 1;
                 } else {
-                    tail = sweep_push4(W, tail, wb, a0 + 128 + lane * 4, lane);
+                    tail = sweep_push4(W, tail, wb, abits, a0 + 128 + lane * 4, lane);
                     part = 0;
                     j += stride; more = j < n_mine;
                 }
@@ -1256,17 +1257,18 @@ __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
             words[0] = x.x; words[1] = x.y; words[2] = x.z; words[3] = x.w;
         }
         const int nrows = tb->n_rows[age];
-        const double *cum = tb->cum_p[age];
+        const uint32_t *cum24 = tb->cum24[age];
 #pragma unroll
         for (uint32_t w = 0; w < 4; w++) {
             bool pass = false;
             uint32_t row = 0;
             if (w < ncnt) {
                 const uint32_t word = words[w];
-                const double u = (double)(word >> 8) * (1.0 / 16777216.0);
-                // linear scan for the first row with u < cum_p; rows below guide[u's top 10 bits] cannot match
+                // u = (word >> 8) / 2^24; linear scan for the first row with u < cum_p, as an integer compare against
+                // ceil(cum_p 2^24); rows below guide[u's top 10 bits] cannot match
+                const uint32_t k24 = word >> 8;
                 row = tb->guide[age][word >> 22];
-                while ((int)row < nrows - 1 && !(u < cum[row])) row++;   // last row on overrun: the reference fails there (p ~ 1e-15)
+                while ((int)row < nrows - 1 && !(k24 < cum24[row])) row++;   // last row on overrun: the reference fails there (p ~ 1e-15)
                 places += 1u << (5 * tb->place[age][row]);               // daily_contacts[place]++ (main.pyx:1571)
                 pass = (int)(word & 255u) < kq;
             }
@@ -1796,6 +1798,11 @@ extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *
         for (int i = 0; i < n_rows[age]; i++) {
             int k = age * RB_MAX_ROWS + i;
             h->cum_p[age][i] = cum_p[k];
+            {   // exact: scaling by 2^24 is exact in double, and for integer k, k < x  <=>  k < ceil(x)
+                double x = cum_p[k] * 16777216.0, cx = (double)(uint64_t)x;
+                if (cx < x) cx += 1.0;
+                h->cum24[age][i] = cx >= 4294967295.0 ? 0xffffffffu : (uint32_t)cx;
+            }
             h->start[age][i] = e->age_start[age_lo[k]];
             h->size[age][i] = e->age_start[age_hi[k] + 1] - e->age_start[age_lo[k]];
             h->place[age][i] = place[k];
