@@ -30,6 +30,17 @@ AREA = 'HUS'
 N_AGENTS = 1685983
 
 
+def load_sweep_traffic(n_replicas):
+    """Mean DRAM bytes (read + write) per k_sweep launch over the 180 launches of one run, from the committed ncu pass
+    (profiles/: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` on every k_sweep launch,
+    tools/collect_profiles.sh).  Only valid for the replica count it was captured at."""
+    p = os.path.join(ROOT, 'profiles', 'r01_launches_and_sweep_traffic_R%d.json' % n_replicas)
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return float(json.load(f)['k_sweep_dram']['mean_traffic_bytes'])
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -275,7 +286,7 @@ def main():
         gpu_launches=int(launches),
         clocks=clocks,
         roofline=dict(bound='hbm', kernel='k_sweep', achieved=roof_achieved, peak=peak_gbs, unit='GB/s',
-                      frac=roof_achieved / peak_gbs, traffic=None, peak_source=peak_src,
+                      frac=roof_achieved / peak_gbs, traffic=load_sweep_traffic(R) if D == 180 else None, peak_source=peak_src,
                       algorithmic_bytes_per_launch=alg['sweep'] / D, avg_launch_ms=sweep_ms,
                       share_of_step=float(kms[1]) / ksum),
         roofline_whole_run=dict(achieved=whole, peak=peak_gbs, unit='GB/s', frac=whole / peak_gbs,
