@@ -32,6 +32,9 @@
 #include "../../include/reina_b200.h"
 #include "rng.cuh"
 
+#ifndef SW_STREAM_DIV
+#define SW_STREAM_DIV 6      // the sweep streams the packed words once more than 1 / 6 of the agents are infected (measured: the bitmap walk wins below)
+#endif
 #define MAX_INFECTEES 64   // main.pyx:128
 #define MAX_CONTACTS 128   // main.pyx:129
 
@@ -724,7 +727,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
         // dense days (> 1/24 of the agents infected) stream the packed words, sparse days walk the activity bitmap
         int infected = 0;
         for (int age = 0; age < G.n_ages; age++) infected += c->counts[RB_A_INFECTED][age];
-        c->stream_mode = (long long)infected * 24 > (long long)G.N ? 1u : 0u;
+        c->stream_mode = (long long)infected * SW_STREAM_DIV > (long long)G.N ? 1u : 0u;
         c->n_q_base = c->n_newq;
     }
     if (G.xbuf) {     // this rank's message header: the sweep and the contact kernel add to it from zero
@@ -1165,7 +1168,12 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
 // (thinning, see the oracle) decides whether the contact can transmit at all.  The few survivors go through a
 // warp-private shared-memory ring and are finished on dense warps: get_person_from_age_range (:1525-1535),
 // person_expose / did_infect (:238-244, 908-934), atomicMin on the target's conflict slot.
-#define EX_THREADS 256
+#ifndef EX_THREADS
+#define EX_THREADS 128
+#endif
+#ifndef EX_CTAS_PER_SM
+#define EX_CTAS_PER_SM 12        // CTAs per SM the grid is sized for: all resident (40 registers), one wave
+#endif
 #define EX_WARPS (EX_THREADS / 32)
 #define EX_RCAP 256
 
@@ -1762,7 +1770,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     int per_rep = sms * SW_CTAS_PER_SM / R; if (per_rep < 1) per_rep = 1;
     e->sweep_blocks = want < per_rep ? want : per_rep; if (e->sweep_blocks < 1) e->sweep_blocks = 1;
     CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 8 x 24 KB per SM
-    e->list_blocks = (sms * 4 + R - 1) / R; if (e->list_blocks < 2) e->list_blocks = 2;
+    e->list_blocks = sms * EX_CTAS_PER_SM / R; if (e->list_blocks < 2) e->list_blocks = 2;
     // k_resolve is a chain of dependent scattered accesses per infection: enough threads for one pass over the day's list
     e->resolve_blocks = (int)((G.N / 128 + 255) / 256); if (e->resolve_blocks < e->list_blocks) e->resolve_blocks = e->list_blocks;
     { int cap = sms * 16 / R; if (cap < 64) cap = 64; if (e->resolve_blocks > cap) e->resolve_blocks = cap; }
@@ -1952,7 +1960,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     while (mid >= GRAPH_DAYS) { CK(cudaGraphLaunch(e->graph[0], e->stream)); mid -= GRAPH_DAYS; e->launches += 4 * GRAPH_DAYS; }
     while (mid > 0) { CK(cudaGraphLaunch(e->graph[1], e->stream)); mid -= 1; e->launches += 4; }
     k_sweep<<<dim3(e->sweep_blocks, R), SW_THREADS, 0, e->stream>>>(G);
-    k_expose<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G);
+    k_expose<<<dim3(e->list_blocks, R), EX_THREADS, 0, e->stream>>>(G);
     k_resolve<false><<<dim3(e->resolve_blocks, R), 256, 0, e->stream>>>(G);
     k_post<<<R, PRE_THREADS, 0, e->stream>>>(G);
     e->launches += 4;
@@ -1975,7 +1983,7 @@ extern "C" int rb_step_profiled(rb_engine *e, int32_t n_days, float *ms_per_kern
         CK(cudaEventRecord(v[0], e->stream));
         k_pre<<<R, PRE_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[1], e->stream));
         k_sweep<<<dim3(e->sweep_blocks, R), SW_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[2], e->stream));
-        k_expose<<<dim3(e->list_blocks, R), 256, 0, e->stream>>>(G); CK(cudaEventRecord(v[3], e->stream));
+        k_expose<<<dim3(e->list_blocks, R), EX_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[3], e->stream));
         k_resolve<false><<<dim3(e->resolve_blocks, R), 256, 0, e->stream>>>(G); CK(cudaEventRecord(v[4], e->stream));
         k_post<<<R, PRE_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[5], e->stream));
         e->launches += 5;
