@@ -79,7 +79,7 @@ struct DevTable {
     uint8_t lo_age[RB_MAX_AGES][RB_MAX_ROWS], hi_age[RB_MAX_AGES][RB_MAX_ROWS];
     uint8_t susc_uniform[RB_MAX_AGES][RB_MAX_ROWS];   // susceptibility identical for every age of the row's band
     uint8_t guide[RB_MAX_AGES][1024];                 // first row whose cum_p exceeds b/1024: start of the row search
-    uint8_t nguide[RB_MAX_AGES][2][64];               // first k with ncdf[k] > b/64: start of the contact-count search
+    uint8_t nguide[RB_MAX_AGES][2][256];              // first k with ncdf[k] > b/256: start of the contact-count search
 };
 
 struct Attempt { uint32_t cand, parent; unsigned long long key; };
@@ -809,10 +809,10 @@ __device__ __forceinline__ void stage_expose(const Eng &G, RepCtr *c, RepCtr *cd
         const int cls = (desc >> 22) & 1u;
         u32x4 x = philox(c->seed, a, (uint32_t)c->day, PU_NCONTACT, 0);
         const double u = u01d(x.x, x.y);
-        // n = first k with u < cdf[k] (k = limit if none); entries below nguide[u's top 6 bits] cannot match
+        // n = first k with u < cdf[k] (k = limit if none); entries below nguide[u's top 8 bits] cannot match
         const double *cdf = tb->ncdf[age][cls];
         const int limit = cls ? 5 : 100;
-        int k = tb->nguide[age][cls][x.x >> 26];
+        int k = tb->nguide[age][cls][x.x >> 24];
         while (k < limit && !(u < __ldg(&cdf[k]))) k++;
         ncont = (uint32_t)k;
         cnt = (ncont + 3u) >> 2;          // work items are groups of four contact slots (they share one Philox block)
@@ -1115,11 +1115,15 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
                     for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
                     const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
                     uint32_t p = tail + incl - mine;
-                    for (uint32_t k = 0; k < mine; k++) {
-                        W.qi[p & (SW_QCAP - 1)] = a0 + (uint32_t)part * 32u + (uint32_t)(__ffs(cw) - 1);
-                        cw &= cw - 1u;
-                        p++;
-                    }
+                    // the active agents' packed words are gathered HERE (the only per-agent gather of the sweep): up to four
+                    // independent loads per lane in flight instead of one per lane in the consumer
+                    uint32_t ia[4], wa[4];
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; k++)
+                        if (k < mine) { ia[k] = a0 + (uint32_t)part * 32u + (uint32_t)(__ffs(cw) - 1); cw &= cw - 1u; wa[k] = G.hot[base + ia[k]]; }
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; k++)
+                        if (k < mine) { W.qi[(p + k) & (SW_QCAP - 1)] = ia[k]; W.qw[(p + k) & (SW_QCAP - 1)] = wa[k]; }
                     tail += tot;
                 }
             }
@@ -1135,8 +1139,7 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
             uint32_t a = 0, h = 0, desc = 0;
             if ((uint32_t)lane < m) {
                 a = W.qi[(head + lane) & (SW_QCAP - 1)];
-                // sparse days: the only per-agent gather of the sweep (~3 % of the agents); dense days: the word came with the stream
-                h = stream ? W.qw[(head + lane) & (SW_QCAP - 1)] : G.hot[gb + a];
+                h = W.qw[(head + lane) & (SW_QCAP - 1)];      // gathered (bitmap walk) or streamed by the producer
                 stage_active_lane(G, r, c, gb, a, h, want_e, want_t, removed, infected_others, desc);
             }
             head += m;
@@ -1825,9 +1828,9 @@ extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *
     }
     for (int age = 0; age < e->cfg.n_ages; age++)
         for (int cls = 0; cls < 2; cls++)
-            for (int b = 0, k = 0; b < 64; b++) {
+            for (int b = 0, k = 0; b < 256; b++) {
                 const int limit = cls ? 5 : 100;
-                while (k < limit && !(h->ncdf[age][cls][k] > (double)b / 64.0)) k++;
+                while (k < limit && !(h->ncdf[age][cls][k] > (double)b / 256.0)) k++;
                 h->nguide[age][cls][b] = (uint8_t)k;
             }
     for (int age = 0; age < e->cfg.n_ages; age++)
