@@ -201,6 +201,14 @@ int32_t rb_shard_rank(rb_engine *e);
 int32_t rb_shard_nranks(rb_engine *e);
 int64_t rb_shard_message_bytes(rb_engine *e);   /* bytes each rank contributes to the daily all-gather */
 
+/* ---- Checkpoint / resume (the reference keeps its state only in process memory).
+ * The blob holds the whole mutable state between two rb_step calls (packed words, agent records, bitmaps, counters, test
+ * queues, stats rows so far, day).  It can be loaded into any engine created with the same inputs, replica count and
+ * max_days; contact tables and the schedule are inputs, not state, and are set by the caller as usual. */
+int64_t rb_state_bytes(rb_engine *e);
+int rb_save_state(rb_engine *e, void *out, int64_t capacity);
+int rb_load_state(rb_engine *e, const void *in, int64_t n_bytes);
+
 /* number of kernel launches issued by this handle so far */
 int64_t rb_launch_count(rb_engine *e);
 const char *rb_last_error(void);

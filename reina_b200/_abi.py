@@ -88,7 +88,9 @@ SYMBOLS = ['create', 'destroy', 'reset', 'step_profiled', 'set_contact_table', '
 
 
 # population-sharded mode: exported by the CUDA library only (the sequential CPU oracle has no ranks)
-SHARD_SYMBOLS = ['shard_unique_id', 'shard_init', 'shard_rank', 'shard_nranks', 'shard_message_bytes']
+SHARD_SYMBOLS = ['shard_unique_id', 'shard_init', 'shard_rank', 'shard_nranks', 'shard_message_bytes',
+                 # checkpoint / resume of the device-resident state
+                 'state_bytes', 'save_state', 'load_state']
 SH_SHIFT = 12      # ownership stripes of 4096 agents, dealt round-robin over the ranks (engine.cu owns())
 
 
@@ -161,6 +163,10 @@ class Library:
             f['shard_nranks'].argtypes = [vp]
             f['shard_message_bytes'].argtypes = [vp]
             f['shard_message_bytes'].restype = C.c_int64
+            f['state_bytes'].argtypes = [vp]
+            f['state_bytes'].restype = C.c_int64
+            f['save_state'].argtypes = [vp, C.c_void_p, C.c_int64]
+            f['load_state'].argtypes = [vp, C.c_void_p, C.c_int64]
         self.f = f
 
     def check(self, rc, what):
@@ -207,6 +213,16 @@ class Engine:
         assert len(unique_id) == 128
         self.lib.check(self.lib.f['shard_init'](self.h, rank, nranks, bytes(unique_id), exchange_capacity), 'shard_init')
         self.rank, self.nranks = rank, nranks
+
+    def save_state(self):
+        n = self.lib.f['state_bytes'](self.h)
+        out = np.empty(n, dtype=np.uint8)
+        self.lib.check(self.lib.f['save_state'](self.h, out.ctypes.data, n), 'save_state')
+        return out
+
+    def load_state(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self.lib.check(self.lib.f['load_state'](self.h, blob.ctypes.data, blob.size), 'load_state')
 
     def close(self):
         if getattr(self, 'h', None):

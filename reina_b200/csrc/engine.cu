@@ -1901,12 +1901,13 @@ extern "C" int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const u
     NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
     Eng &G = e->G;
     // message capacities: this rank's share of the agents; a day's state changes / transmissions / tests / capacity
-    // events are small fractions of it (peak of the reference epidemic: ~1.3 % / 0.5 % / 0.2 % / 0.02 % of the agents)
+    // events are small fractions of it (peak day of the reference epidemic: 0.9 % / 0.5 % / 0.17 % / 0.08 % of the
+    // agents; ~2.3x headroom each, exchange_capacity scales them, overflow is a loud RB_OTHER_FAILURE)
     const double share = (double)G.N / nranks * (exchange_capacity > 0 ? exchange_capacity : 1.0);
-    G.xcap_upd = (uint32_t)(share / 16) + 4096;
-    G.xcap_succ = (uint32_t)(share / 48) + 4096;
-    G.xcap_q = (uint32_t)(share / 64) + 2048;
-    G.xcap_ev = (uint32_t)(share / 256) + 2048;
+    G.xcap_upd = (uint32_t)(share / 48) + 4096;
+    G.xcap_succ = (uint32_t)(share / 96) + 4096;
+    G.xcap_q = (uint32_t)(share / 256) + 2048;
+    G.xcap_ev = (uint32_t)(share / 512) + 2048;
     G.xslot = xslot_bytes(G.xcap_q, G.xcap_ev, G.xcap_upd, G.xcap_succ);
     if (dalloc(e, &G.xbuf, G.xslot * nranks)) return 1;
     CK(cudaMemset(G.xbuf, 0, G.xslot * nranks));
@@ -2120,5 +2121,63 @@ extern "C" int rb_read_available(rb_engine *e, int32_t replica, int32_t *o) {
     CK(cudaStreamSynchronize(e->stream));
     RepCtr c; CK(cudaMemcpy(&c, &e->G.ctr[replica], sizeof c, cudaMemcpyDeviceToHost));
     o[0] = c.avail_beds; o[1] = c.avail_icu;
+    return 0;
+}
+
+// ---------------------------------------------------------------- checkpoint / resume
+// The reference keeps its state only in process memory (no checkpointing); a device-resident run
+// of many replicas is worth saving.  The blob is the engine's whole mutable state between two rb_step calls.
+struct StateHeader {
+    uint64_t magic; int32_t version, n_agents, n_replicas, n_ages, row_len, max_days, day, sus_words;
+    uint32_t cap_queue; uint32_t seed; int32_t rec_bytes, ctr_bytes;
+};
+#define STATE_MAGIC 0x3030324252414e49ull      // "INARB200"
+struct StatePart { void *dev; size_t bytes; };
+static std::vector<StatePart> state_parts(rb_engine *e) {
+    const Eng &G = e->G;
+    const size_t RN = (size_t)G.R * G.Npad, RW = (size_t)G.R * G.sus_words, RQ = (size_t)G.R * 2 * G.cap_queue;
+    return {
+        {G.hot, RN * sizeof(uint32_t)}, {G.rec, RN * sizeof(AgentRec)}, {G.sus, RW * sizeof(uint32_t)}, {G.act, RW * sizeof(uint32_t)},
+        {G.ctr, (size_t)G.R * sizeof(RepCtr)}, {G.q_key, RQ * sizeof(unsigned long long)}, {G.q_agent, RQ * sizeof(int32_t)},
+        {G.stats, (size_t)G.R * (G.max_days + 1) * G.row_len * sizeof(int32_t)},
+    };
+}
+static StateHeader state_header(rb_engine *e) {
+    const Eng &G = e->G;
+    StateHeader h; memset(&h, 0, sizeof h);
+    h.magic = STATE_MAGIC; h.version = 1; h.n_agents = G.N; h.n_replicas = G.R; h.n_ages = G.n_ages; h.row_len = G.row_len;
+    h.max_days = G.max_days; h.day = e->day; h.sus_words = G.sus_words; h.cap_queue = G.cap_queue; h.seed = e->cfg.seed;
+    h.rec_bytes = (int32_t)sizeof(AgentRec); h.ctr_bytes = (int32_t)sizeof(RepCtr);
+    return h;
+}
+
+extern "C" int64_t rb_state_bytes(rb_engine *e) {
+    size_t n = sizeof(StateHeader);
+    for (const StatePart &p : state_parts(e)) n += p.bytes;
+    return (int64_t)n;
+}
+
+extern "C" int rb_save_state(rb_engine *e, void *out, int64_t capacity) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (capacity < rb_state_bytes(e)) { snprintf(g_err, sizeof g_err, "rb_save_state: buffer of %lld bytes, need %lld", (long long)capacity, (long long)rb_state_bytes(e)); return 1; }
+    CK(cudaStreamSynchronize(e->stream));
+    uint8_t *o = (uint8_t *)out;
+    const StateHeader h = state_header(e);
+    memcpy(o, &h, sizeof h); o += sizeof h;
+    for (const StatePart &p : state_parts(e)) { CK(cudaMemcpy(o, p.dev, p.bytes, cudaMemcpyDeviceToHost)); o += p.bytes; }
+    return 0;
+}
+
+extern "C" int rb_load_state(rb_engine *e, const void *in, int64_t n_bytes) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (n_bytes != rb_state_bytes(e)) { snprintf(g_err, sizeof g_err, "rb_load_state: %lld bytes, this engine's state is %lld", (long long)n_bytes, (long long)rb_state_bytes(e)); return 1; }
+    StateHeader h; memcpy(&h, in, sizeof h);
+    StateHeader w = state_header(e); w.day = h.day; w.seed = h.seed;
+    if (memcmp(&h, &w, sizeof h) != 0) { snprintf(g_err, sizeof g_err, "rb_load_state: the blob was saved by an engine of another shape (agents / replicas / max_days / build)"); return 1; }
+    if (h.day < 0 || h.day > e->cfg.max_days) { snprintf(g_err, sizeof g_err, "rb_load_state: bad day"); return 1; }
+    CK(cudaStreamSynchronize(e->stream));
+    const uint8_t *o = (const uint8_t *)in + sizeof h;
+    for (const StatePart &p : state_parts(e)) { CK(cudaMemcpy(p.dev, o, p.bytes, cudaMemcpyHostToDevice)); o += p.bytes; }
+    e->day = h.day; e->cfg.seed = h.seed;
     return 0;
 }

@@ -469,6 +469,19 @@ class Context:
         self.day = 0
         self._state_day = -1
 
+    def save_state(self):
+        """Checkpoint: the engine's whole device state between two iterate() calls as one uint8 array (np.save it).
+        Interventions, inputs and max_days are not part of it: load it into a Context built the same way."""
+        return self._engine.save_state()
+
+    def load_state(self, blob):
+        """Resume from a save_state() blob: this Context continues at the saved day."""
+        self._engine.load_state(blob)
+        self.day = self._engine.day()
+        self._state_day = -1
+        while len(self._plan) < self.day:         # replays the host half (interventions, contact tables) up to that day
+            self._plan_next_day()
+
     def upload_inputs(self):
         """Re-send every contact table to the device (bench.py: per-step host->device input copy)."""
         for epoch, t in self._tables.items():

@@ -126,3 +126,30 @@ def test_sampler_parity(cuda_lib, oracle_lib):
                  'hospitalization_period', 'icu_period', 'onset_to_removed_period'):
         for age, sev in ((5, 'MILD'), (45, 'SEVERE'), (85, 'CRITICAL'), (70, 'FATAL')):
             assert np.array_equal(gpu.sample(what, age, sev), cpu.sample(what, age, sev)), (what, age, sev)
+
+
+def test_checkpoint_resume(cuda_lib, oracle_lib):
+    """save_state() in the middle of a run, load_state() into a fresh Context: the resumed run is bit-identical to
+    the uninterrupted one (and to the oracle), stats rows of the days before the checkpoint included."""
+    counts = helpers.small_population(60000)
+    v = helpers.inputs.default_variables()
+    v['hospital_beds'], v['icu_units'] = 20, 2
+    kw = dict(variables=v, age_count_override=counts, seed=21, interventions=helpers.stress_interventions(), n_replicas=2)
+    a = helpers.make_context(cuda_lib, **kw)
+    a.run(47)
+    blob = a.save_state()
+    a.run(43)
+    b = helpers.make_context(cuda_lib, **kw)
+    b.load_state(blob)
+    assert b.day == 47 and b.get_date_for_today() == '2020-04-05'
+    b.run(43)
+    assert np.array_equal(a.series(0, 90), b.series(0, 90))
+    for r in range(2):
+        assert np.array_equal(a._engine.read_agents(r), b._engine.read_agents(r))
+        assert np.array_equal(a._engine.read_queue(r), b._engine.read_queue(r))
+    cpu = helpers.make_context(oracle_lib, **dict(kw, n_replicas=1))
+    cpu.run(90)
+    assert np.array_equal(cpu.series(0, 90)[0], b.series(0, 90)[0])
+    other = helpers.make_context(cuda_lib, **dict(kw, n_replicas=1))
+    with pytest.raises(helpers._abi.EngineError):
+        other.load_state(blob)                      # a blob of two replicas does not fit an engine of one
