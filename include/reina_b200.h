@@ -131,6 +131,11 @@ void rb_destroy(rb_engine *e);
  * Context(random_seed=seed), main.pyx:1759-1781) without reallocating; schedule and contact tables are kept. */
 int rb_reset(rb_engine *e, uint32_t seed);
 
+/* Population.set_initial_state (main.pyx:1452-1516, called by Context.__init__ :1780-1781): start the run with an
+ * epidemic already under way.  ipc = {dead, in_icu, in_ward, confirmed_cases, incubating, ill, recovered}
+ * (InitialPopulationCondition, calc/datasets.py:107-135).  Once, before the first rb_step; rb_reset re-applies it. */
+int rb_set_initial_state(rb_engine *e, const int32_t *ipc7);
+
 /* ContactMatrix.generate_contact_probabilities output (main.pyx:1184-1235) for one mobility epoch:
  * per participant age `n_rows[age]` rows of {cum_p, contact band [lo,hi], place, mask_p}, arrays are
  * [n_ages][RB_MAX_ROWS]; nr_contacts[age] = nr_contacts_by_age (main.pyx:1209-1211).

@@ -40,7 +40,7 @@
 #define MAX_CONTACTS 128   /* main.pyx:129 */
 
 enum { PU_START = 1, PU_NCONTACT, PU_CONTACT, PU_SEVERITY, PU_INCUB, PU_ONSET, PU_SEEK, PU_NOBED,
-       PU_TRACE, PU_IMPORT, PU_PERM, PU_SAMPLE, PU_CONTACT2 };
+       PU_TRACE, PU_IMPORT, PU_PERM, PU_SAMPLE, PU_CONTACT2, PU_INIT };
 #define KEY1 0x5EEDB200u
 
 typedef struct {
@@ -97,6 +97,7 @@ struct rb_engine {
     int32_t row_len;
     int feistel_half;
     float last_ms;
+    int32_t ipc[7]; int has_ipc;   /* initial population condition, re-applied by ro_reset */
 };
 
 static char g_err[256];
@@ -671,9 +672,47 @@ static void init_replica(rb_engine *e, int ri, uint32_t seed) {
     r->p_successful_tracing = 1.0f;
 }
 
+/* Population.set_initial_state, main.pyx:1452-1516 (called by Context.__init__ :1780-1781 while testing is still
+ * NO_TESTING and day == 0).  ipc = {dead, in_icu, in_ward, confirmed_cases, incubating, ill, recovered}
+ * (InitialPopulationCondition, calc/datasets.py:107-135).  Literal restatement, quirks included: people are drawn with
+ * replacement and infected whatever their state (get_random_person :1518-1523), recovered_without_illness() equals
+ * `incubating`, person_transfer_to_icu follows person_hospitalize unconditionally, all_detected is cleared for ages
+ * 0..99 only and the confirmed cases are spread one per age. */
+static void apply_initial_state(rb_engine *e, Replica *r) {
+    const int32_t dead = e->ipc[0], in_icu = e->ipc[1], in_ward = e->ipc[2], confirmed = e->ipc[3];
+    const int32_t incubating = e->ipc[4], ill = e->ipc[5], recovered = e->ipc[6];
+    const int32_t were_ill = dead + recovered + in_icu + in_ward + ill, were_incubating = were_ill + incubating;
+    const int32_t i_incubating = incubating, i_rws = i_incubating + (were_incubating - were_ill);
+    const int32_t i_ill_at_home = i_rws + ill, i_dead = i_ill_at_home + dead, i_in_icu = i_dead + in_icu, i_in_ward = i_in_icu + in_ward;
+    for (int32_t i = 0; i < were_incubating; i++) {
+        uint32_t x[4];
+        philox(r->seed, KEY1, (uint32_t)i, 0, PU_INIT, 0, x);
+        const int32_t ai = (int32_t)(x[0] % (uint32_t)e->cfg.n_agents);
+        Agent *p = &r->agents[ai];
+        person_infect(e, r, ai, -1, 0, 0);
+        if (i < i_incubating) continue;
+        if (i < i_rws) { person_recover(r, p); continue; }
+        person_become_ill(e, r, ai);
+        if (i < i_ill_at_home) continue;
+        if (i < i_dead) { person_die(r, p); continue; }
+        if (i < i_in_icu) { person_hospitalize(e, r, ai); person_transfer_to_icu(e, r, ai); continue; }
+        if (i < i_in_ward) { person_hospitalize(e, r, ai); continue; }
+        person_recover(r, p);
+    }
+    for (int age = 0; age < 100 && age < e->cfg.n_ages; age++) r->counts[RB_A_ALL_DETECTED][age] = 0;
+    for (int32_t i = 0; i < confirmed; i++) r->counts[RB_A_ALL_DETECTED][(100 + i) % 100] += 1;
+}
+
+int ro_set_initial_state(rb_engine *e, const int32_t *ipc7) {
+    if (e->day != 0) { snprintf(g_err, sizeof g_err, "set_initial_state: only before the first step"); return 1; }
+    memcpy(e->ipc, ipc7, sizeof e->ipc); e->has_ipc = 1;
+    for (int ri = 0; ri < e->cfg.n_replicas; ri++) apply_initial_state(e, &e->rep[ri]);
+    return 0;
+}
+
 int ro_reset(rb_engine *e, uint32_t seed) {
     e->cfg.seed = seed; e->day = 0;
-    for (int ri = 0; ri < e->cfg.n_replicas; ri++) init_replica(e, ri, seed);
+    for (int ri = 0; ri < e->cfg.n_replicas; ri++) { init_replica(e, ri, seed); if (e->has_ipc) apply_initial_state(e, &e->rep[ri]); }
     return 0;
 }
 

@@ -82,7 +82,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # REINA_B200_LIB: measurement aid (tools/variants.sh builds the library with different tuning macros)
 CUDA_LIB_PATH = os.environ.get('REINA_B200_LIB') or os.path.join(_HERE, 'libreina_b200.so')
 
-SYMBOLS = ['create', 'destroy', 'reset', 'step_profiled', 'set_contact_table', 'set_schedule', 'step', 'sync', 'day',
+SYMBOLS = ['create', 'destroy', 'reset', 'set_initial_state', 'step_profiled', 'set_contact_table', 'set_schedule', 'step', 'sync', 'day',
            'snapshot', 'row_len', 'read_stats', 'read_moments', 'read_per_age', 'problem', 'sample', 'read_agents',
            'read_queue', 'read_available', 'last_step_ms', 'launch_count', 'last_error']
 
@@ -133,6 +133,7 @@ class Library:
         f['set_schedule'].argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(DayParams)]
         f['step'].argtypes = [vp, C.c_int32]
         f['reset'].argtypes = [vp, C.c_uint32]
+        f['set_initial_state'].argtypes = [vp, C.POINTER(C.c_int32)]
         f['step_profiled'].argtypes = [vp, C.c_int32, C.POINTER(C.c_float)]
         f['sync'].argtypes = [vp]
         f['day'].argtypes = [vp]
@@ -249,6 +250,11 @@ class Engine:
 
     def step(self, n=1):
         self.lib.check(self.lib.f['step'](self.h, n), 'step')
+
+    def set_initial_state(self, ipc7):
+        a = np.ascontiguousarray(ipc7, dtype=np.int32)
+        assert a.size == 7
+        self.lib.check(self.lib.f['set_initial_state'](self.h, _ptr(a, C.c_int32)), 'set_initial_state')
 
     def reset(self, seed):
         self.lib.check(self.lib.f['reset'](self.h, int(seed) & 0xFFFFFFFF), 'reset')

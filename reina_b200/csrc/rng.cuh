@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 enum { PU_START = 1, PU_NCONTACT, PU_CONTACT, PU_SEVERITY, PU_INCUB, PU_ONSET, PU_SEEK, PU_NOBED,
-       PU_TRACE, PU_IMPORT, PU_PERM, PU_SAMPLE, PU_CONTACT2 };
+       PU_TRACE, PU_IMPORT, PU_PERM, PU_SAMPLE, PU_CONTACT2, PU_INIT };
 #define RB_KEY1 0x5EEDB200u
 
 struct u32x4 { uint32_t x, y, z, w; };

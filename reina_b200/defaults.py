@@ -40,6 +40,10 @@ VARIABLE_DEFAULTS = {
     'ratio_of_duration_before_hospitalisation': 30.0,
     'ratio_of_duration_in_ward': 15.0,
     'imported_infection_ages': [[0, 15.0], [20, 40.0], [40, 40.0], [60, 5.0], [70, 0]],
+    # variables.py:362-364: the unmeasurable part of the initial population condition (calc/datasets.py:166-168)
+    'incubating_at_simulation_start': 0,
+    'ill_at_simulation_start': 0,
+    'recovered_at_simulation_start': 0,
     'interventions': [
         ['test-all-with-symptoms', '2020-02-20'],
         ['test-only-severe-symptoms', '2020-03-15', 25],

@@ -135,6 +135,42 @@ def create_disease_params(variables):
     return kwargs
 
 
+class InitialPopulationCondition:
+    """calc/datasets.py:107-135."""
+
+    def __init__(self, dead=0, in_icu=0, in_ward=0, confirmed_cases=0, infected_cases=0, incubating=0, ill=0, recovered=0):
+        self.dead, self.in_icu, self.in_ward, self.confirmed_cases = int(dead), int(in_icu), int(in_ward), int(confirmed_cases)
+        self.infected_cases, self.incubating, self.ill, self.recovered = int(infected_cases), int(incubating), int(ill), int(recovered)
+
+    def has_initial_state(self):
+        return bool(self.dead or self.in_icu or self.in_ward or self.confirmed_cases or self.infected_cases
+                    or self.incubating or self.ill or self.recovered)
+
+    def were_ill(self):
+        return self.dead + self.recovered + self.in_icu + self.in_ward + self.ill
+
+    def were_incubating(self):
+        return self.were_ill() + self.incubating
+
+    def recovered_without_illness(self):
+        return self.were_incubating() - self.were_ill()
+
+
+def initial_population_condition(variables, area=None):
+    """get_initial_population_condition, calc/datasets.py:143-173: hospital figures of the start date from the area's
+    case file, the unmeasurable ones from the variables; a start date the file does not hold gives the empty
+    condition (the reference prints a note and does the same, :151-156)."""
+    area = area or variables['area_name']
+    row = _inputs().get('cases', {}).get(area, {}).get(variables['start_date'])
+    if row is None:
+        return InitialPopulationCondition()
+    dead, in_icu, in_ward, confirmed = row
+    return InitialPopulationCondition(
+        dead=dead, in_icu=in_icu, in_ward=in_ward, confirmed_cases=confirmed,
+        ill=variables.get('ill_at_simulation_start', 0), incubating=variables.get('incubating_at_simulation_start', 0),
+        recovered=variables.get('recovered_at_simulation_start', 0))
+
+
 def build_context_args(variables=None, area=None, age_count_override=None):
     """Arguments of model.Context as simulate_individuals builds them, with numpy inputs.
 
@@ -147,7 +183,7 @@ def build_context_args(variables=None, area=None, age_count_override=None):
     pop_params = dict(
         age_structure={int(a): int(n) for a, n in enumerate(counts)},
         contacts_per_day=contacts_long(v['max_age']),
-        initial_population_condition=None,
+        initial_population_condition=initial_population_condition(v, area),
         age_groups=make_age_groups(v['max_age']),
         imported_infection_ages=v['imported_infection_ages'],
     )

@@ -247,9 +247,6 @@ class Context:
                  shard=None, _library=None):
         lib = _library if _library is not None else _abi.cuda_library()
         ipc = population_params.pop('initial_population_condition', None)   # main.pyx:1765 (mutates, as the reference)
-        if ipc is not None and getattr(ipc, 'has_initial_state', lambda: False)():
-            # set_initial_state (main.pyx:1452-1516) is not exercised by any benchmark config (SURVEY 8a note 5)
-            raise NotImplementedError('initial_population_condition with a non-empty state is not supported')
 
         age_structure = population_params['age_structure']
         items = list(age_structure.items())
@@ -298,6 +295,9 @@ class Context:
         cfg.max_days, cfg.n_import_classes, cfg.device = int(max_days), len(lo), int(device)
         cfg.contact_capacity = float(contact_capacity)
         self._engine = _abi.Engine(lib, cfg, age_counts, group_of_age[:n_ages], variants, lo, hi, cum)
+        if ipc is not None and ipc.has_initial_state():      # main.pyx:1780-1781
+            self._engine.set_initial_state([getattr(ipc, k) for k in
+                                            ('dead', 'in_icu', 'in_ward', 'confirmed_cases', 'incubating', 'ill', 'recovered')])
         if shard is not None:
             # population-sharded mode: shard = (rank, nranks, nccl_unique_id[, exchange_capacity]); every rank builds the
             # same Context (same inputs, interventions and seed) on its own GPU and makes the same calls

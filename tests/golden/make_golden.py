@@ -30,6 +30,13 @@ CONFIGS = {
     'hus_mitigation': ('HUS', 'mitigation', 180),
     'hus_summer_boogie': ('HUS', 'summer-boogie', 180),
     'hus_looser_restrictions': ('HUS', 'looser-restrictions-to-start-with', 180),
+    # Population.set_initial_state (main.pyx:1452-1516): a start date the HUS case file holds (9 dead, 32 in ICU, 52 in
+    # ward, 1200 confirmed) + the example values of variables.py:212-214 for the unmeasurable part
+    'hus_initial_state': ('HUS', None, 180),
+}
+VARIABLE_OVERRIDES = {
+    'hus_initial_state': dict(start_date='2020-04-01', incubating_at_simulation_start=150, ill_at_simulation_start=50,
+                              recovered_at_simulation_start=1000),
 }
 
 
@@ -44,8 +51,13 @@ def main():
         area, scenario, days = CONFIGS[name]
         t0 = time.time()
         seeds = np.arange(a.seed0, a.seed0 + a.seeds)
+        variables = None
+        if name in VARIABLE_OVERRIDES:
+            from reina_b200 import inputs
+            variables = inputs.default_variables()
+            variables.update(VARIABLE_OVERRIDES[name])
         series, t_iter, wall = ref_harness.run_ensemble(seeds, days=days, processes=a.processes,
-                                                        area=area, scenario=scenario)
+                                                        area=area, scenario=scenario, variables=variables)
         out = os.path.join(HERE, 'ref_ensemble_%s.npz' % name)
         np.savez_compressed(
             out, mean=series.mean(axis=0), std=series.std(axis=0, ddof=1), n=len(seeds),

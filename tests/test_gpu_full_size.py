@@ -19,10 +19,16 @@ GOLD = os.path.join(helpers.ROOT, 'tests', 'golden')
     ('hus_hammer_and_dance', 'HUS', 'hammer-and-dance'),           # configs[2]: contact tracing 30 -> 60 %
     ('hus_mitigation', 'HUS', 'mitigation'),                       # configs[2]: capacity building + mobility
     ('hus_summer_boogie', 'HUS', 'summer-boogie'),
+    ('hus_initial_state', 'HUS', None),                            # Population.set_initial_state, start 2020-04-01
 ])
 def test_ensemble_statistics_match_reference(cuda_lib, gold_name, area, scenario):
     gold = np.load(os.path.join(GOLD, 'ref_ensemble_%s.npz' % gold_name))
-    ctx = helpers.make_context(cuda_lib, area=area, scenario=scenario, seed=424242, n_replicas=64, max_days=181)
+    variables = None
+    if gold_name == 'hus_initial_state':
+        from test_oracle_pinned import INITIAL_STATE_VARIABLES
+        variables = helpers.inputs.default_variables()
+        variables.update(INITIAL_STATE_VARIABLES)
+    ctx = helpers.make_context(cuda_lib, area=area, scenario=scenario, seed=424242, n_replicas=64, max_days=181, variables=variables)
     ctx.run(180)
     mine = helpers.series_matrix(ctx)
     ctx.close()

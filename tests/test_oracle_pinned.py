@@ -56,6 +56,38 @@ def test_ensemble_means_within_3_standard_errors():
         assert abs(z[-1, names.index(s)]) < 3.0, (s, z[-1, names.index(s)])
 
 
+INITIAL_STATE_VARIABLES = dict(start_date='2020-04-01', incubating_at_simulation_start=150, ill_at_simulation_start=50,
+                               recovered_at_simulation_start=1000)      # tests/golden/make_golden.py, 'hus_initial_state'
+
+
+def _oracle_run_initial_state(seed):
+    v = helpers.inputs.default_variables()
+    v.update(INITIAL_STATE_VARIABLES)
+    ctx = helpers.make_context(helpers.oracle_library(), area='HUS', variables=v, seed=seed, max_days=121)
+    ctx.run(120)
+    return helpers.series_matrix(ctx)[0]
+
+
+def test_initial_population_condition_matches_reference():
+    """Population.set_initial_state (main.pyx:1452-1516): HUS started on 2020-04-01 from the case file's hospital
+    figures + 150 incubating / 50 ill / 1000 recovered.  Day 0 is deterministic in its totals (they must agree exactly);
+    the 120 days that follow agree within 3 standard errors (16 oracle seeds vs 64 reference seeds)."""
+    gold = np.load(os.path.join(GOLD, 'ref_ensemble_hus_initial_state.npz'))
+    with ProcessPoolExecutor(min(8, os.cpu_count() or 1)) as ex:
+        mine = np.stack(list(ex.map(_oracle_run_initial_state, [8100 + s for s in range(16)])))
+    names = list(gold['names'])
+    g = {k: (gold[k][:120] if k in ('mean', 'std') else gold[k]) for k in ('mean', 'std', 'n')}
+    z, exact = zscores(mine, g)
+    assert not exact.any(), 'deterministic cells differ: %s' % sorted({(int(d), names[j]) for d, j in np.argwhere(exact)})[:10]
+    for s, want in (('all_infected', 1293), ('dead', 9), ('in_icu', 32), ('in_ward', 52), ('recovered', 1000)):
+        assert mine[:, 0, names.index(s)].tolist() == [want] * 16 and gold['mean'][0, names.index(s)] == want, s
+    # all_detected is cleared for ages 0..99 only (main.pyx:1505-1506): a hospitalised 100-year-old leaves 1201
+    assert 1200 <= mine[:, 0, names.index('all_detected')].min() and mine[:, 0, names.index('all_detected')].max() <= 1202
+    assert (np.abs(z) > 3).mean() < 0.015 and np.abs(z).max() < 5.0, np.abs(z).max()
+    for s in ('all_infected', 'dead', 'all_detected', 'recovered', 'cum_icu'):
+        assert abs(z[-1, names.index(s)]) < 3.0, (s, z[-1, names.index(s)])
+
+
 def _chi2_same(a, b, min_expected=20):
     """Two count histograms drawn from the same distribution? (pooled bins, chi-square contingency test)"""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)

@@ -65,10 +65,24 @@ def contact_matrix(country='FI', max_age=100):
     return dict(contact_bands=bands, rows=out)
 
 
+def case_files():
+    """data/hosp_cases_<area>.csv (calc/datasets.py:80-84): date -> [dead, in_icu, in_ward, confirmed], the inputs of
+    get_initial_population_condition (:143-173)."""
+    out = {}
+    for area, name in (('HUS', 'hosp_cases_hus.csv'), ('Varsinais-Suomi', 'hosp_cases_varsinais-suomi.csv')):
+        rows = {}
+        with open(os.path.join(REF, 'data', name)) as f:
+            for r in csv.DictReader(f):
+                rows.setdefault(r['date'], [int(float(r[k] or 0)) for k in ('dead', 'in_icu', 'in_ward', 'confirmed')])
+        out[area] = rows
+    return out
+
+
 def main():
     data = dict(
         areas={a: population_by_age(a) for a in MUNICIPALITIES},
         contacts=contact_matrix(),
+        cases=case_files(),
     )
     for a, c in data['areas'].items():
         print(a, sum(c), file=sys.stderr)
