@@ -177,7 +177,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--replicas', type=int, default=128, help='ensemble members (seeds) per GPU')
+    ap.add_argument('--replicas', type=int, default=256, help='ensemble members (seeds) per GPU (BASELINE configs[3]: 256 seeds)')
     ap.add_argument('--days', type=int, default=180)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -278,7 +278,7 @@ def main():
             workload='HUS 1,685,983 agents x %d days, default interventions (BASELINE configs[1]), ensemble of %d seeds per GPU '
                      'advanced by the same launches (configs[3] share)' % (D, R),
             replicas_per_gpu=R, days=D, agents=N_AGENTS, parallelism='ensemble x%d' % world,
-            l2='inputs larger than L2 (%.1f GB of agent state per GPU)' % (R * N_AGENTS * 34 / 1e9) if R > 2 else
+            l2='inputs larger than L2 (%.1f GB of agent state per GPU)' % (R * N_AGENTS * 36.3 / 1e9) if R > 2 else
                'single 6.7 MB packed-state array is L2-resident by nature of the workload (180 dependent days)',
         ),
         e2e=dict(value=e2e_value, unit='agent-days/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
