@@ -161,7 +161,7 @@ __device__ void write_stats_row(const Eng &G, int r, RepCtr *c, int32_t *srow /*
 // Up to IMP_CHUNK imports are settled at once, one per thread: each takes its first susceptible draw; if all picks
 // of the chunk are distinct (checked through the agents' conflict slots) that IS the sequential result, otherwise
 // (probability ~ chunk^2 / N) one thread replays the chunk in order.  Called by the whole CTA.
-#define IMP_CHUNK 1024
+#define IMP_CHUNK PRE_THREADS
 __device__ __forceinline__ int32_t import_draw(const Eng &G, const RepCtr *c, size_t base, uint32_t ord, uint32_t t) {
     u32x4 x = philox(c->seed, ord, (uint32_t)c->day, PU_IMPORT | (t << 8), 0);
     float p = u01f(x.x);

@@ -49,7 +49,9 @@
 enum { EV_HOSP_CLAIM = 0, EV_WARD_RELEASE = 1, EV_TO_ICU = 2, EV_ICU_RELEASE = 3 };
 
 #define SORT_SMEM 2048
-#define PRE_THREADS 1024
+#ifndef PRE_THREADS
+#define PRE_THREADS 512       // day-boundary CTA: two fit on an SM, so 256 replicas are one wave
+#endif
 #define NEG_INF (-(1 << 29))
 
 struct DevTable {
