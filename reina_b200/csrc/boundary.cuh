@@ -573,14 +573,14 @@ __device__ void post_body(const Eng &G, const int r, SmemSmall &S) {
     }
 }
 
-__global__ void __launch_bounds__(PRE_THREADS) k_pre(Eng G) { __shared__ SmemSmall S; pre_body(G, blockIdx.x, S); }
-__global__ void __launch_bounds__(PRE_THREADS) k_post(Eng G) { __shared__ SmemSmall S; post_body(G, blockIdx.x, S); }
+__global__ void __launch_bounds__(PRE_THREADS) k_pre(Eng G) { __shared__ SmemSmall S; pre_body(G, blockIdx.x + G.r0, S); }
+__global__ void __launch_bounds__(PRE_THREADS) k_post(Eng G) { __shared__ SmemSmall S; post_body(G, blockIdx.x + G.r0, S); }
 // end of day d (capacity scan) fused with the start of day d+1 (stats row, queue, tracing, ...): one launch less per day
 __global__ void __launch_bounds__(PRE_THREADS) k_between(Eng G) {
     __shared__ SmemSmall S;
-    post_body(G, blockIdx.x, S);
+    post_body(G, blockIdx.x + G.r0, S);
     __syncthreads();
-    pre_body(G, blockIdx.x, S);
+    pre_body(G, blockIdx.x + G.r0, S);
 }
 
 #endif

@@ -70,7 +70,7 @@ __device__ __forceinline__ void expose_survivors(const Eng &G, int r, RepCtr *c,
 __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
     __shared__ int s_place[RB_N_PLACES];
     __shared__ uint32_t s_ri[EX_WARPS][EX_RCAP], s_rx[EX_WARPS][EX_RCAP];
-    const int r = blockIdx.y;
+    const int r = blockIdx.y + G.r0;
     RepCtr *c = &G.ctr[r];
     const DevTable *tb = G.tables[c->epoch];
     const uint32_t n = min(c->n_items, G.cap_items);
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
 // by the boundary at the point where the reference drains, so every stats row is unchanged.
 template <bool DRAIN>
 __global__ void __launch_bounds__(256) k_resolve(Eng G) {
-    const int r = blockIdx.y;
+    const int r = blockIdx.y + G.r0;
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
     const uint32_t n = min(c->n_succ, G.cap_succ);

@@ -28,6 +28,15 @@
 static thread_local char g_err[512];
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return 1; } } while (0)
 
+#define MAX_GROUPS 8
+struct ReplicaGroup {
+    int r0, R;                          // replicas [r0, r0 + R)
+    int sweep_blocks, list_blocks, resolve_blocks;
+    cudaStream_t stream;
+    cudaEvent_t ev_stagger, ev_join;
+    cudaGraphExec_t graph[2];
+};
+
 struct rb_engine {
     rb_config cfg;
     Eng G;
@@ -47,6 +56,12 @@ struct rb_engine {
     int sweep_blocks, list_blocks, resolve_blocks;
     cudaGraphExec_t graph[2];
     bool have_graphs;
+    // replica groups: the ensemble is split into n_groups sets of replicas, each advanced by its own chain of launches
+    // on its own stream with a grid sized for its share of the SMs.  The groups run half a day apart, so the
+    // latency-bound phases of one (k_resolve, the single-CTA day boundary) overlap the sweep / contact kernels of another.
+    int n_groups;
+    ReplicaGroup grp[MAX_GROUPS];
+    cudaEvent_t ev_fork;
     ncclComm_t comm;                    // population-sharded mode
     int merge_blocks;
     Ipc ipc; bool has_ipc;              // initial population condition, re-applied by rb_reset
@@ -115,11 +130,20 @@ static int init_counters(rb_engine *e, uint32_t seed) {
     return 0;
 }
 
+static int setup_groups(rb_engine *e, int sms);
+
 extern "C" void rb_destroy(rb_engine *e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
-    if (e->have_graphs) { cudaGraphExecDestroy(e->graph[0]); cudaGraphExecDestroy(e->graph[1]); }
+    if (e->have_graphs) {
+        if (e->n_groups <= 1) { cudaGraphExecDestroy(e->graph[0]); cudaGraphExecDestroy(e->graph[1]); }
+        else for (int g = 0; g < e->n_groups; g++) { cudaGraphExecDestroy(e->grp[g].graph[0]); cudaGraphExecDestroy(e->grp[g].graph[1]); }
+    }
+    for (int g = 0; g < e->n_groups && e->n_groups > 1; g++) {
+        cudaStreamDestroy(e->grp[g].stream); cudaEventDestroy(e->grp[g].ev_stagger); cudaEventDestroy(e->grp[g].ev_join);
+    }
+    if (e->n_groups > 1) cudaEventDestroy(e->ev_fork);
     if (e->comm) g_nccl.CommDestroy(e->comm);
     for (void *p : e->allocs) cudaFree(p);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
@@ -139,9 +163,10 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
         snprintf(g_err, sizeof g_err, "no CUDA device: reina_b200 has no CPU fallback"); return 2;
     }
     CK(cudaSetDevice(cfg->device));
+    if (const char *s = getenv("RB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(s));   // measurement aid
     rb_engine *e = new rb_engine();
     e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0; e->have_graphs = false; e->comm = nullptr; e->merge_blocks = 1;
-    e->has_ipc = false;
+    e->has_ipc = false; e->n_groups = 1;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     Eng &G = e->G;
@@ -212,7 +237,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     int want = (G.sus_words / 4 + SW_WARPS * 32 - 1) / (SW_WARPS * 32);
     int per_rep = sms * SW_CTAS_PER_SM / R; if (per_rep < 1) per_rep = 1;
     e->sweep_blocks = want < per_rep ? want : per_rep; if (e->sweep_blocks < 1) e->sweep_blocks = 1;
-    CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 8 x 24 KB per SM
+    CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 9 x 24 KB per SM
     e->list_blocks = sms * EX_CTAS_PER_SM / R; if (e->list_blocks < 2) e->list_blocks = 2;
     // k_resolve is a chain of dependent scattered accesses per infection: enough threads for one pass over the day's list
     e->resolve_blocks = (int)((G.N / 128 + 255) / 256); if (e->resolve_blocks < e->list_blocks) e->resolve_blocks = e->list_blocks;
@@ -220,7 +245,41 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     k_init<<<dim3(e->sweep_blocks, R), 256, 0, e->stream>>>(G); e->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
+    if (setup_groups(e, sms)) { rb_destroy(e); return 1; }
     *out = e;
+    return 0;
+}
+
+// Replica groups (see rb_engine).  Measured on B200 (HUS, 256 replicas, ms per 180-day step): 1 group 162.7; 2 groups
+// with full-wave grids 154.9; 3 x 100 % 152.6; 4 x 50 % 153.0; 4 x 100 % 152.2; 8 x 50 % 156.0 -- the grids are
+// oversubscribed on purpose, a group in its latency-bound phase leaves its share of the SMs to the others.
+// RB_GROUPS / RB_GROUP_WAVE_PCT override (measurement aid).  Each group's grid covers `pct` % of one wave.
+static int setup_groups(rb_engine *e, int sms) {
+    const int R = e->G.R;
+    int ng = R >= 128 ? 4 : (R >= 32 ? 2 : 1), pct = R >= 128 ? 50 : 100;
+    if (const char *s = getenv("RB_GROUPS")) ng = atoi(s);
+    if (const char *s = getenv("RB_GROUP_WAVE_PCT")) pct = atoi(s);
+    if (pct < 1) pct = 100;
+    if (ng > MAX_GROUPS) ng = MAX_GROUPS;
+    if (ng > R) ng = R;
+    if (ng < 1) ng = 1;
+    e->n_groups = ng;
+    if (ng == 1) return 0;
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    const Eng &G = e->G;
+    const int want = (G.sus_words / 4 + SW_WARPS * 32 - 1) / (SW_WARPS * 32);
+    for (int g = 0; g < ng; g++) {
+        ReplicaGroup &q = e->grp[g];
+        q.r0 = (int)((long long)R * g / ng); q.R = (int)((long long)R * (g + 1) / ng) - q.r0;
+        int per = sms * SW_CTAS_PER_SM * pct / 100 / q.R; if (per < 1) per = 1;
+        q.sweep_blocks = want < per ? want : per;
+        q.list_blocks = sms * EX_CTAS_PER_SM * pct / 100 / q.R; if (q.list_blocks < 2) q.list_blocks = 2;
+        q.resolve_blocks = (int)((G.N / 128 + 255) / 256); if (q.resolve_blocks < q.list_blocks) q.resolve_blocks = q.list_blocks;
+        { int cap = sms * 16 * pct / 100 / q.R; if (cap < 64) cap = 64; if (q.resolve_blocks > cap) q.resolve_blocks = cap; }
+        CK(cudaStreamCreateWithFlags(&q.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&q.ev_stagger, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&q.ev_join, cudaEventDisableTiming));
+    }
     return 0;
 }
 
@@ -320,8 +379,32 @@ static void launch_segment(rb_engine *e, cudaStream_t st) {
 
 // No kernel takes the day as an argument (each replica carries its own day counter and reads the schedule from
 // device memory), so a captured graph of GRAPH_DAYS segments is replayed for any stretch of days.
+static void launch_group_segment(rb_engine *e, const ReplicaGroup &q, bool stagger_mark) {
+    Eng G = e->G; G.r0 = q.r0;
+    k_sweep<<<dim3(q.sweep_blocks, q.R), SW_THREADS, 0, q.stream>>>(G);
+    k_expose<<<dim3(q.list_blocks, q.R), EX_THREADS, 0, q.stream>>>(G);
+    if (stagger_mark) cudaEventRecord(q.ev_stagger, q.stream);       // the next group starts its day here
+    k_resolve<true><<<dim3(q.resolve_blocks, q.R), 256, 0, q.stream>>>(G);
+    k_between<<<q.R, PRE_THREADS, 0, q.stream>>>(G);
+}
+
 #define GRAPH_DAYS 16
 static int build_graphs(rb_engine *e) {
+    if (e->n_groups > 1) {
+        for (int g = 0; g < e->n_groups; g++)
+            for (int which = 0; which < 2; which++) {
+                ReplicaGroup &q = e->grp[g];
+                int nseg = which == 0 ? GRAPH_DAYS : 1;
+                cudaGraph_t gr;
+                CK(cudaStreamBeginCapture(q.stream, cudaStreamCaptureModeThreadLocal));
+                for (int i = 0; i < nseg; i++) launch_group_segment(e, q, false);
+                CK(cudaStreamEndCapture(q.stream, &gr));
+                CK(cudaGraphInstantiate(&q.graph[which], gr, 0));
+                CK(cudaGraphDestroy(gr));
+            }
+        e->have_graphs = true;
+        return 0;
+    }
     for (int which = 0; which < 2; which++) {
         int nseg = which == 0 ? GRAPH_DAYS : 1;
         cudaGraph_t g;
@@ -407,6 +490,32 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
         CK(cudaEventRecord(e->ev0, e->stream));
         k_pre<<<1, PRE_THREADS, 0, e->stream>>>(G); e->launches++;
         for (int d = 0; d < n_days; d++) if (launch_day_sharded(e, d == n_days - 1)) return 1;
+        CK(cudaEventRecord(e->ev1, e->stream));
+        CK(cudaGetLastError());
+        e->day += n_days;
+        return 0;
+    }
+    if (e->n_groups > 1) {
+        CK(cudaEventRecord(e->ev0, e->stream));
+        k_pre<<<R, PRE_THREADS, 0, e->stream>>>(G); e->launches++;
+        CK(cudaEventRecord(e->ev_fork, e->stream));
+        for (int g = 0; g < e->n_groups; g++) {
+            ReplicaGroup &q = e->grp[g];
+            CK(cudaStreamWaitEvent(q.stream, e->ev_fork, 0));
+            int mid = n_days - 1;
+            if (g > 0 && mid > 0) CK(cudaStreamWaitEvent(q.stream, e->grp[g - 1].ev_stagger, 0));     // half a day behind the previous group
+            if (mid > 0) { launch_group_segment(e, q, g + 1 < e->n_groups); mid -= 1; e->launches += 4; }
+            while (mid >= GRAPH_DAYS) { CK(cudaGraphLaunch(q.graph[0], q.stream)); mid -= GRAPH_DAYS; e->launches += 4 * GRAPH_DAYS; }
+            while (mid > 0) { CK(cudaGraphLaunch(q.graph[1], q.stream)); mid -= 1; e->launches += 4; }
+            Eng Gq = G; Gq.r0 = q.r0;
+            k_sweep<<<dim3(q.sweep_blocks, q.R), SW_THREADS, 0, q.stream>>>(Gq);
+            k_expose<<<dim3(q.list_blocks, q.R), EX_THREADS, 0, q.stream>>>(Gq);
+            k_resolve<false><<<dim3(q.resolve_blocks, q.R), 256, 0, q.stream>>>(Gq);
+            k_post<<<q.R, PRE_THREADS, 0, q.stream>>>(Gq);
+            e->launches += 4;
+            CK(cudaEventRecord(q.ev_join, q.stream));
+            CK(cudaStreamWaitEvent(e->stream, q.ev_join, 0));
+        }
         CK(cudaEventRecord(e->ev1, e->stream));
         CK(cudaGetLastError());
         e->day += n_days;

@@ -144,6 +144,7 @@ struct Eng {
     // population-sharded mode (rb_shard_init): every rank holds the whole state, sweeps and exposes only the agents
     // it owns, and publishes what the others must know in its slot of the exchange buffer (one all-gather per day)
     int32_t rank, nranks;
+    int32_t r0;                                    // first replica of this launch (replica groups on concurrent streams, engine.cu)
     uint8_t *xbuf; size_t xslot;                   // [nranks] message slots; slot `rank` is written locally
     uint32_t xcap_q, xcap_ev, xcap_upd, xcap_succ;
 };

@@ -27,7 +27,7 @@
 #define SW_PFD 3             // packed-word chunks in flight per warp (cp.async), 1 KB each; 0 = plain loads
 #endif
 #ifndef SW_CTAS_PER_SM
-#define SW_CTAS_PER_SM 8
+#define SW_CTAS_PER_SM 9     // 56 registers; measured 6 / 8 / 9 / 10 / 12 CTAs per SM: 170.0 / 162.7 / 159.0 / 161.0 / 165.7 ms per HUS step
 #endif
 
 struct WarpRings {
@@ -251,6 +251,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src,
     const int nbytes = valid ? 16 : 0;      // src-size 0: nothing is read, the 16 bytes are zero-filled
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(nbytes) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
 #if SW_PFD > 0
     __shared__ uint4 s_pf[SW_WARPS][SW_PFD][2][32];
 #endif
-    const int r = blockIdx.y;
+    const int r = blockIdx.y + G.r0;
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
     const DevTable *tb = G.tables[c->epoch];
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
     const int stride = gridDim.x * SW_WARPS;
     const bool stream = c->stream_mode != 0;
     uint32_t head = 0, tail = 0, e_head = 0, e_tail = 0, t_head = 0, t_tail = 0;
+    uint32_t ready = 0;                     // bitmap walk: ring A entries below `ready` were committed before the latest gather group
 
     // ---- producer state.  Dense day: the packed words are streamed, 256 agents (1 KB) per warp step, in two halves of
     // 128 so that ring A never takes more than 128 entries at once.  Sparse day: one bit per agent says whether the
@@ -308,6 +313,14 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
     uint32_t cw = 0, a0 = 0, abits = 0;
     int part = 0;                           // dense: 0 = load a chunk, 1 = second half pending; sparse: word of `wb` in `cw` (4 = none)
     if (!stream) part = 4;
+    // bitmap walk: the activity vector of the NEXT warp step is loaded one step ahead
+    auto load_act = [&](int jj) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (jj < n_mine) { const int vi = (nrk == 1 ? jj : jj * nrk + rk) * 32 + lane; if (vi < n_vec) v = __ldg(&act4[vi]); }
+        return v;
+    };
+    uint4 nb = make_uint4(0, 0, 0, 0);
+    if (!stream) nb = load_act(j);
 #if SW_PFD > 0
     uint4 (*pf)[2][32] = s_pf[warp];
     int slot = 0;
@@ -331,7 +344,7 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
 
     for (;;) {
         // ---------------- produce
-        while (more && tail - head < 32) {
+        while (more && (stream ? tail : ready) - head < 32) {
             if (stream) {
                 if (part == 0) {
                     const int chunk = chunk_of(j);
@@ -366,8 +379,8 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
                     const int v0 = (nrk == 1 ? j : j * nrk + rk) * 32;
                     j += stride;
                     const int vi = v0 + lane;
-                    wb = make_uint4(0, 0, 0, 0);
-                    if (vi < n_vec) wb = __ldg(&act4[vi]);
+                    wb = nb;
+                    nb = load_act(j);
                     a0 = (uint32_t)vi * 128u;
                     if (__any_sync(0xffffffffu, (wb.x | wb.y | wb.z | wb.w) != 0u)) { part = 0; cw = wb.x; }
                     else more = j < n_mine;
@@ -375,6 +388,10 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
                     part++;
                     cw = part == 1 ? wb.y : (part == 2 ? wb.z : wb.w);
                     if (part == 4) more = j < n_mine;
+                } else if (tail - head > SW_QCAP - 128) {
+                    // no room for another round of up to 128 entries: everything queued becomes consumable
+                    cp_async_wait<0>();
+                    ready = tail;
                 } else {
                     // every lane queues up to 4 of its set bits per round: at most 128 pushes, the ring holds 256
                     const uint32_t mine = min(__popc(cw), 4);
@@ -383,22 +400,30 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
                     for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
                     const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
                     uint32_t p = tail + incl - mine;
-                    // the active agents' packed words are gathered HERE (the only per-agent gather of the sweep): up to four
-                    // independent loads per lane in flight instead of one per lane in the consumer
-                    uint32_t ia[4], wa[4];
+                    // the active agents' packed words are gathered HERE (the only per-agent gather of the sweep), as
+                    // asynchronous 4-byte copies straight into the ring: the producer never waits for them, the consumer
+                    // waits for all but the latest round's group, so the gathers of several rounds are in flight while
+                    // earlier batches run through the stages
 #pragma unroll
                     for (uint32_t k = 0; k < 4; k++)
-                        if (k < mine) { ia[k] = a0 + (uint32_t)part * 32u + (uint32_t)(__ffs(cw) - 1); cw &= cw - 1u; wa[k] = G.hot[base + ia[k]]; }
-#pragma unroll
-                    for (uint32_t k = 0; k < 4; k++)
-                        if (k < mine) { W.qi[(p + k) & (SW_QCAP - 1)] = ia[k]; W.qw[(p + k) & (SW_QCAP - 1)] = wa[k]; }
+                        if (k < mine) {
+                            const uint32_t ia = a0 + (uint32_t)part * 32u + (uint32_t)(__ffs(cw) - 1); cw &= cw - 1u;
+                            W.qi[(p + k) & (SW_QCAP - 1)] = ia;
+                            cp_async4(&W.qw[(p + k) & (SW_QCAP - 1)], G.hot + base + ia);
+                        }
+                    cp_async_commit();
+                    ready = tail;
                     tail += tot;
                 }
             }
             __syncwarp();
         }
         // ---------------- consume: full batches while the source lasts, whatever is left afterwards
-        const uint32_t av = tail - head;
+        if (!stream) {
+            if (more) cp_async_wait<1>(); else { cp_async_wait<0>(); ready = tail; }
+            __syncwarp();
+        }
+        const uint32_t av = (stream ? tail : ready) - head;
         if (av) {
             const uint32_t m = min(32u, av);
             const size_t gb = base;
