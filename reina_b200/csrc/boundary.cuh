@@ -5,6 +5,44 @@
 #define REINA_B200_BOUNDARY_CUH
 #include "state.cuh"
 
+// ---------------------------------------------------------------- the team that runs one replica's day boundary
+// Narrow: one CTA (ensembles: a GPU full of replicas, one CTA each).  Wide: `ncta` co-resident CTAs of a cooperative
+// launch joined by a grid barrier (few replicas of a large population: a day's test queue, tracing attempts and
+// capacity events run to 10^5 entries at 5 x 10^7 agents, far too many for one CTA).  The heavy phases stride over
+// the whole team; the small sequential ones stay on the lead CTA.  A wide launch falls back to its lead CTA alone on
+// days with little to do (RepCtr::wide_day, decided by k_resolve), so quiet days pay for no grid barrier.
+struct Team {
+    uint32_t tid, nth;          // thread index / thread count across the team
+    uint32_t cta, ncta;
+    bool lead;                  // this CTA runs the sequential phases
+    unsigned int *bar;          // grid barrier word (RepCtr::wide_bar), zero at kernel entry and exit
+    unsigned int gen;           // barriers passed
+};
+__device__ __forceinline__ Team team_of(RepCtr *c, uint32_t cta, uint32_t ncta) {
+    Team T;
+    T.cta = cta; T.ncta = ncta; T.lead = cta == 0; T.bar = &c->wide_bar; T.gen = 0;
+    T.tid = cta * blockDim.x + threadIdx.x; T.nth = ncta * blockDim.x;
+    return T;
+}
+__device__ __forceinline__ void team_sync(Team &T) {
+    __syncthreads();
+    if (T.ncta > 1) {
+        T.gen++;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(T.bar, 1u);
+            const unsigned int target = T.gen * T.ncta;
+            while (*(volatile unsigned int *)T.bar < target) { }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+}
+// last statement of a team kernel: leaves the barrier word at zero for the next launch
+__device__ __forceinline__ void team_finish(Team &T) {
+    if (T.ncta > 1) { team_sync(T); if (T.tid == 0) *T.bar = 0u; }
+}
+
 // ---------------------------------------------------------------- block-wide helpers (single CTA)
 // Bitonic sort of (key, val) pairs, ascending by key; n <= SORT_SMEM sorts in shared memory, larger lists in
 // place in global memory (capacity must be a power of two >= n; the tail is padded with KEY_IDLE).
@@ -130,6 +168,93 @@ __device__ bool block_bucket_sort(unsigned long long *keys, int32_t *vals, uint3
     return true;
 }
 
+// The same sort by a whole team.  Narrow teams use the single-CTA version; a wide team keeps the bucket counters in
+// global scratch, builds the histogram and scatters with every thread, scans the counters on the lead CTA, and lets
+// every thread order and write back whole buckets.  Falls back to the lead CTA's bitonic sort if scratch is too small.
+__device__ void team_sort_pairs(Team &T, unsigned long long *keys, int32_t *vals, uint32_t n, uint32_t cap, Attempt *scratch, uint32_t scratch_cap,
+                                BucketMap bm, unsigned long long *sk, int32_t *sv, int *warp_sums) {
+    if (T.ncta == 1) {
+        if (n > 1 && !block_bucket_sort(keys, vals, n, scratch, scratch_cap, bm, sv, warp_sums)) block_sort_pairs(keys, vals, n, cap, sk, sv);
+        __syncthreads();
+        return;
+    }
+    if (n <= 1) return;
+    uint32_t B = SORT_BUCKETS;
+    while (B < n && B < SORT_BUCKETS_MAX) B <<= 1;
+    // the segmented scan below needs B / ncta to be a power of two: teams whose size is not one sort on the lead CTA
+    if (2ull * n + B / 4 + WIDE_MAX_CTAS / 4 + 1 > scratch_cap || (T.ncta & (T.ncta - 1)) != 0 || B / T.ncta < 4) {
+        if (T.lead) { if (!block_bucket_sort(keys, vals, n, scratch, scratch_cap, bm, sv, warp_sums)) block_sort_pairs(keys, vals, n, cap, sk, sv); }
+        team_sync(T);
+        return;
+    }
+    bm.B = B;
+    int32_t *cnt = (int32_t *)(scratch + 2ull * n);
+    for (uint32_t b = T.tid; b < B; b += T.nth) cnt[b] = 0;
+    team_sync(T);
+    for (uint32_t i = T.tid; i < n; i += T.nth) {
+        const unsigned long long k = keys[i];
+        const uint32_t b = min(bucket_of(bm, k), B - 1u);
+        const uint32_t slot = (uint32_t)atomicAdd(&cnt[b], 1);
+        scratch[i].key = k; scratch[i].cand = (uint32_t)vals[i]; scratch[i].parent = b | (slot << 16);
+    }
+    team_sync(T);
+    // exclusive scan of the counters: every CTA scans its own contiguous B / ncta of them (4 consecutive counters per
+    // thread and pass) and publishes its total; the offsets of the CTAs before it are added where the scan is used
+    int32_t *ctot = cnt + B;                                 // [ncta] totals, right behind the counters
+    const uint32_t seg = B / T.ncta, s0 = T.cta * seg;       // B and ncta are powers of two / divide evenly (checked by the caller)
+    {
+        int run = 0;
+        for (uint32_t t0 = 0; t0 < seg; t0 += 4u * blockDim.x) {
+            const uint32_t b = s0 + t0 + 4u * threadIdx.x;
+            int4 v = make_int4(0, 0, 0, 0);
+            if (t0 + 4u * threadIdx.x < seg) v = *reinterpret_cast<const int4 *>(cnt + b);
+            const int mine = v.x + v.y + v.z + v.w;
+            int total;
+            int ex = block_scan_incl(mine, &total, warp_sums) - mine + run;
+            if (t0 + 4u * threadIdx.x < seg) {
+                int4 o; o.x = ex; o.y = ex + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
+                *reinterpret_cast<int4 *>(cnt + b) = o;
+            }
+            run += total;
+        }
+        if (threadIdx.x == 0) ctot[T.cta] = run;
+    }
+    team_sync(T);
+    if (threadIdx.x < 32) {                                  // offsets of the segments: prefix over <= 64 CTA totals, kept in shared memory
+        int acc = 0;
+        for (uint32_t k0 = 0; k0 < T.ncta; k0 += 32) {
+            const uint32_t k = k0 + threadIdx.x;
+            int v = k < T.ncta ? ctot[k] : 0, incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+            if (k < T.ncta) sv[k] = acc + incl - v;
+            acc += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+    const int32_t *segoff = sv;
+    uint32_t seg_shift = 0; while ((1u << seg_shift) < seg) seg_shift++;
+    Attempt *out = scratch + n;
+    for (uint32_t i = T.tid; i < n; i += T.nth) {
+        const Attempt e = scratch[i];
+        const uint32_t b = e.parent & 0xffffu;
+        out[segoff[b >> seg_shift] + cnt[b] + (e.parent >> 16)] = e;
+    }
+    team_sync(T);
+    for (uint32_t b = T.tid; b < B; b += T.nth) {          // insertion sort inside each bucket, written straight back
+        const uint32_t lo = (uint32_t)(segoff[b >> seg_shift] + cnt[b]);
+        const uint32_t hi = b + 1 < B ? (uint32_t)(segoff[(b + 1) >> seg_shift] + cnt[b + 1]) : n;
+        for (uint32_t i = lo + 1; i < hi; i++) {
+            const Attempt e = out[i];
+            uint32_t j = i;
+            while (j > lo && out[j - 1].key > e.key) { out[j] = out[j - 1]; j--; }
+            out[j] = e;
+        }
+        for (uint32_t i = lo; i < hi; i++) { keys[i] = out[i].key; vals[i] = (int32_t)out[i].cand; }
+    }
+    team_sync(T);
+}
+
 // Context.generate_state, main.pyx:1813-1857: fold per-age counters into age groups + scalars.
 __device__ void write_stats_row(const Eng &G, int r, RepCtr *c, int32_t *srow /* shared, >= row_len */) {
     int day = c->day;
@@ -236,8 +361,8 @@ __device__ __forceinline__ bool trace_eligible(uint32_t h) {   // queue_for_test
     return H_STATE(h) != RB_DEAD && !(h & (H_DET | H_QUEUED));
 }
 
-#define TS(k) do { if (G.dbg == 9 && threadIdx.x == 0) { long long now_ = clock64(); c->dbg_t[k] += now_ - c->dbg_last; c->dbg_last = now_; } } while (0)
-// ---------------------------------------------------------------- day boundary (1 CTA per replica)
+#define TS(k) do { if (G.dbg == 9 && T.tid == 0) { long long now_ = clock64(); c->dbg_t[k] += now_ - c->dbg_last; c->dbg_last = now_; } } while (0)
+// ---------------------------------------------------------------- day boundary (one team per replica)
 struct MP { int a, b; };
 struct SmemSmall {
     unsigned long long sk[SORT_SMEM];
@@ -248,9 +373,10 @@ struct SmemSmall {
     } u;
     int warp_sums[32];
     int sh_i[4];
+    MP pre_bed, pre_icu;
 };
 
-__device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
+__device__ void pre_body(const Eng &G, const int r, SmemSmall &S, Team &T) {
     unsigned long long *sk = S.sk; int32_t *sv = S.sv; int32_t *srow = S.u.srow; int *warp_sums = S.warp_sums; int *sh_i = S.sh_i;
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
@@ -258,55 +384,60 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
     const rb_day_params *dp = &G.sched[day];
     const int tid = threadIdx.x;
 
-    if (G.dbg == 9 && threadIdx.x == 0) c->dbg_last = clock64();
-    write_stats_row(G, r, c, srow);
-    TS(0);
-
-    // apply_intervention effects dated today (main.pyx:1880-1960), then Population.init_day (:1687-1699)
-    if (tid == 0) {
-        c->testing_mode = dp->testing_mode;
-        c->p_detected_anyway = dp->p_detected_anyway;
-        c->p_successful_tracing = dp->p_successful_tracing;
-        c->beds += dp->beds_delta; c->avail_beds += dp->beds_delta;
-        c->icu += dp->icu_delta; c->avail_icu += dp->icu_delta;
-    }
-    __syncthreads();
-    int ordinal = 0;       // uniform across the CTA
-    for (int i = 0; i < dp->n_imports; i++)
-        import_infections(G, r, c, dp->import_amount[i], dp->import_variant[i], &ordinal, sv, &sh_i[2]);
-    __syncthreads();
-    for (int i = tid; i < G.n_ages; i += blockDim.x) { c->counts[RB_A_NEW_INFECTIONS][i] = 0; c->counts[RB_A_DETECTED][i] = 0; }
-    if (tid < RB_N_PLACES) c->daily_contacts[tid] = 0;
-    if (tid < RB_MAX_VARIANTS) c->by_variant[tid] = 0;
-    __syncthreads();
-    if (tid == 0) { c->epoch = dp->table_epoch; c->total_infectors = 0; c->total_infections = 0; c->exposed_per_day = 0; }
-    for (int v = 0; v < G.n_variants; v++)
-        if (dp->trickle[v]) import_infections(G, r, c, dp->trickle[v], v, &ordinal, sv, &sh_i[2]);
-    __syncthreads();
-
-    TS(1);   // imports + init_day
-    // HealthcareSystem.iterate (main.pyx:514-558): drain yesterday's queue
+    // queue bookkeeping read before anybody changes it
     const uint32_t cur = c->qsel, nxt = cur ^ 1u;
     unsigned long long *qk = G.q_key + ((size_t)r * 2 + cur) * G.cap_queue;
     int32_t *qa = G.q_agent + ((size_t)r * 2 + cur) * G.cap_queue;
     unsigned long long *nk = G.q_key + ((size_t)r * 2 + nxt) * G.cap_queue;
     int32_t *na = G.q_agent + ((size_t)r * 2 + nxt) * G.cap_queue;
     const uint32_t nq = c->n_queue;
+
+    if (G.dbg == 9 && T.tid == 0) c->dbg_last = clock64();
+    if (T.lead) {      // the small sequential phases: one CTA
+        write_stats_row(G, r, c, srow);
+        TS(0);
+
+        // apply_intervention effects dated today (main.pyx:1880-1960), then Population.init_day (:1687-1699)
+        if (tid == 0) {
+            c->testing_mode = dp->testing_mode;
+            c->p_detected_anyway = dp->p_detected_anyway;
+            c->p_successful_tracing = dp->p_successful_tracing;
+            c->beds += dp->beds_delta; c->avail_beds += dp->beds_delta;
+            c->icu += dp->icu_delta; c->avail_icu += dp->icu_delta;
+        }
+        __syncthreads();
+        int ordinal = 0;       // uniform across the CTA
+        for (int i = 0; i < dp->n_imports; i++)
+            import_infections(G, r, c, dp->import_amount[i], dp->import_variant[i], &ordinal, sv, &sh_i[2]);
+        __syncthreads();
+        for (int i = tid; i < G.n_ages; i += blockDim.x) { c->counts[RB_A_NEW_INFECTIONS][i] = 0; c->counts[RB_A_DETECTED][i] = 0; }
+        if (tid < RB_N_PLACES) c->daily_contacts[tid] = 0;
+        if (tid < RB_MAX_VARIANTS) c->by_variant[tid] = 0;
+        __syncthreads();
+        if (tid == 0) { c->epoch = dp->table_epoch; c->total_infectors = 0; c->total_infections = 0; c->exposed_per_day = 0; }
+        for (int v = 0; v < G.n_variants; v++)
+            if (dp->trickle[v]) import_infections(G, r, c, dp->trickle[v], v, &ordinal, sv, &sh_i[2]);
+        __syncthreads();
+        TS(1);   // imports + init_day
+        if (tid == 0) { c->ct_cases = (int32_t)nq; c->n_newq = 0; c->n_l0 = 0; c->n_l1 = 0; c->n_edges = 0; }
+    }
+    team_sync(T);
+
+    // HealthcareSystem.iterate (main.pyx:514-558): drain yesterday's queue
     const bool ct = c->testing_mode == RB_ALL_WITH_SYMPTOMS_CT;
-    if (tid == 0) { c->ct_cases = (int32_t)nq; c->n_newq = 0; c->n_l0 = 0; c->n_l1 = 0; c->n_edges = 0; }
     if (ct && nq > 1) {                                            // queue order only matters for tracing
         BucketMap bm; bm.n_agents = (uint32_t)G.N; bm.n_prev = c->n_queue_prev; bm.kind = 1;
-        if (!block_bucket_sort(qk, qa, nq, G.succ + (size_t)r * G.cap_succ, G.cap_succ, bm, sv, warp_sums))
-            block_sort_pairs(qk, qa, nq, G.cap_queue, sk, sv);
+        team_sort_pairs(T, qk, qa, nq, G.cap_queue, G.succ + (size_t)r * G.cap_succ, G.cap_succ, bm, sk, sv, warp_sums);
     }
-    __syncthreads();
+    TS(10);  // queue sort
     if (c->drained) {      // k_resolve already marked the queued agents detected: book the counts here, where the reference drains
-        for (int age = tid; age < G.n_ages; age += blockDim.x) {
-            const int d = c->drain_det[age];
-            if (d) { c->counts[RB_A_DETECTED][age] += d; c->counts[RB_A_ALL_DETECTED][age] += d; c->drain_det[age] = 0; }
-        }
+        if (T.lead)
+            for (int age = tid; age < G.n_ages; age += blockDim.x) {
+                const int d = c->drain_det[age];
+                if (d) { c->counts[RB_A_DETECTED][age] += d; c->counts[RB_A_ALL_DETECTED][age] += d; c->drain_det[age] = 0; }
+            }
     } else
-    for (uint32_t i = tid; i < nq; i += blockDim.x) {
+    for (uint32_t i = T.tid; i < nq; i += T.nth) {
         int32_t a = qa[i];
         uint32_t h = G.hot[base + a];
         if (h & H_DET) set_problem(c, RB_WRONG_STATE);   // person_detect, main.pyx:294-298
@@ -314,8 +445,8 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
         int age = age_of(G, a);
         count_add(c, RB_A_DETECTED, age, 1); count_add(c, RB_A_ALL_DETECTED, age, 1);
     }
-    __syncthreads();
-    if (tid == 0) c->drained = 0u;
+    team_sync(T);
+    if (T.tid == 0) c->drained = 0u;
 
     TS(2);   // queue drain
     if (ct && nq > 0) {
@@ -326,7 +457,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
         Attempt *l1 = (Attempt *)(G.items + (size_t)r * G.cap_items);
         const uint32_t cap_l1 = G.cap_items / 2;
         const float ptr = c->p_successful_tracing;
-        for (uint32_t i = tid; i < nq; i += blockDim.x) {
+        for (uint32_t i = T.tid; i < nq; i += T.nth) {
             int32_t x = qa[i];
             int32_t cand[MAX_INFECTEES + 1]; int first;
             int n = trace_candidates(G, base, x, G.hot[base + x], cand, &first);
@@ -341,9 +472,10 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
                 else set_problem(c, RB_OTHER_FAILURE);
             }
         }
-        __syncthreads();
+        team_sync(T);
+        TS(5);   // tracing: level-0 attempts
         uint32_t n0 = min(c->n_l0, G.cap_succ);
-        for (uint32_t j = tid; j < n0; j += blockDim.x) {
+        for (uint32_t j = T.tid; j < n0; j += T.nth) {
             Attempt at = l0[j];
             if (G.rec[base + (at.cand)].winner != at.key) continue;
             int32_t x = (int32_t)at.cand;
@@ -359,22 +491,23 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
                 else set_problem(c, RB_OTHER_FAILURE);
             }
         }
-        __syncthreads();
+        team_sync(T);
         uint32_t n1 = min(c->n_l1, cap_l1);
         // kill edges: a level-1 attempt that precedes the level-0 winner of the same candidate
         uint32_t *esrc = (uint32_t *)(G.ev_key + (size_t)r * G.cap_events);
         uint32_t *edst = (uint32_t *)(G.ev_agent + (size_t)r * G.cap_events);
         const uint32_t cap_e = G.cap_events;
-        for (uint32_t k = tid; k < n1; k += blockDim.x) {
+        for (uint32_t k = T.tid; k < n1; k += T.nth) {
             unsigned long long w = G.rec[base + (l1[k].cand)].winner;
             if (w != KEY_IDLE && l1[k].key < w) {
                 uint32_t idx = atomicAdd(&c->n_edges, 1u);
                 if (idx < cap_e) { esrc[idx] = l1[k].parent; edst[idx] = l1[k].cand; } else set_problem(c, RB_OTHER_FAILURE);
             }
         }
-        __syncthreads();
+        team_sync(T);
+        TS(6);   // tracing: level-1 attempts, kill edges
         uint32_t ne = min(c->n_edges, cap_e);
-        if (ne > 0 && tid == 0) {
+        if (ne > 0 && T.tid == 0) {
             // decide candidates in increasing order of their level-0 key: a candidate loses its tracing rights iff
             // some level-1 attempt from a tracer that kept its rights precedes its own level-0 attempt
             for (;;) {
@@ -394,28 +527,30 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
                 G.rec[base + (edst[k])].winner = (w & CT_DEAD) ? KEY_IDLE : (w & CT_KEYMASK);
             }
         }
-        __syncthreads();
-        for (uint32_t k = tid; k < n1; k += blockDim.x) {
+        if (ne > 0) team_sync(T);
+        TS(7);   // tracing: cyclic dependencies (one thread)
+        for (uint32_t k = T.tid; k < n1; k += T.nth) {
             Attempt e = l1[k];
             if (G.rec[base + (e.parent)].winner == (e.key & ~127ull)) atomicMin(&G.rec[base + (e.cand)].winner, e.key);
         }
-        __syncthreads();
-        for (uint32_t j = tid; j < n0 + n1; j += blockDim.x) {
+        team_sync(T);
+        for (uint32_t j = T.tid; j < n0 + n1; j += T.nth) {
             Attempt e = j < n0 ? l0[j] : l1[j - n0];
             if (G.rec[base + (e.cand)].winner != e.key) continue;
             if (j >= n0 && G.rec[base + (e.parent)].winner != (e.key & ~127ull)) continue;
             uint32_t idx = atomicAdd(&c->n_newq, 1u);
             if (idx < G.cap_queue) { nk[idx] = e.key; na[idx] = (int32_t)e.cand; } else set_problem(c, RB_OTHER_FAILURE);
-            G.hot[base + e.cand] |= H_QUEUED;
+            atomicOr(&G.hot[base + e.cand], H_QUEUED);
         }
-        __syncthreads();
-        for (uint32_t j = tid; j < n0 + n1; j += blockDim.x) { Attempt e = j < n0 ? l0[j] : l1[j - n0]; G.rec[base + (e.cand)].winner = KEY_IDLE; }
-        __syncthreads();
+        team_sync(T);
+        for (uint32_t j = T.tid; j < n0 + n1; j += T.nth) { Attempt e = j < n0 ? l0[j] : l1[j - n0]; G.rec[base + (e.cand)].winner = KEY_IDLE; }
+        team_sync(T);
     }
 
     TS(3);   // contact tracing
     // vaccinate_people (main.pyx:560-583): top-down walk of the age-sorted range; eligibility only ever turns
     // off (dead / vaccinated / detected), so a per-programme cursor below which the walk resumes is exact.
+    if (T.lead)
     for (int p = 0; p < dp->n_vacc; p++) {
         int nr = dp->vacc_nr[p];
         if (!nr) continue;
@@ -450,7 +585,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
     __syncthreads();
 
     TS(4);   // vaccination
-    if (tid == 0) {
+    if (T.tid == 0) {
         u32x4 x = philox(c->seed, 0u, (uint32_t)day, PU_START, 0);     // _iterate_people, main.pyx:1988
         c->start = x.x % (uint32_t)G.N;
         c->n_items = 0; c->n_succ = 0; c->n_events = 0;
@@ -463,7 +598,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S) {
     }
     if (G.xbuf) {     // this rank's message header: the sweep and the contact kernel add to it from zero
         uint32_t *hw = (uint32_t *)xslot_of(G, G.rank).hdr;
-        for (int i = tid; i < (int)(sizeof(RepCtr) / 4); i += blockDim.x) hw[i] = 0u;
+        for (uint32_t i = T.tid; i < (uint32_t)(sizeof(RepCtr) / 4); i += T.nth) hw[i] = 0u;
     }
 }
 
@@ -486,7 +621,7 @@ __device__ __forceinline__ MP mp_icu(int type) {
 }
 __device__ __forceinline__ int mp_apply(MP f, int x) { int t = x + f.a; return t > f.b ? t : f.b; }
 
-__device__ void post_body(const Eng &G, const int r, SmemSmall &S) {
+__device__ void post_body(const Eng &G, const int r, SmemSmall &S, Team &T) {
     unsigned long long *sk = S.sk; int32_t *sv = S.sv; MP *s_bed = S.u.scan.bed, *s_icu = S.u.scan.icu;
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
@@ -495,15 +630,17 @@ __device__ void post_body(const Eng &G, const int r, SmemSmall &S) {
     unsigned long long *ek = G.ev_key + (size_t)r * G.cap_events;
     int32_t *ea = G.ev_agent + (size_t)r * G.cap_events;
     const int day = c->day;
-    if (G.dbg == 9 && threadIdx.x == 0) c->dbg_last = clock64();
+    const int beds0 = c->avail_beds, icu0 = c->avail_icu;
+    const uint32_t n_newq = c->n_newq;
+    if (G.dbg == 9 && T.tid == 0) c->dbg_last = clock64();
     if (n > 0) {
         BucketMap bm; bm.n_agents = (uint32_t)G.N; bm.n_prev = 0; bm.kind = 0;
-        if (n > 1 && !block_bucket_sort(ek, ea, n, G.succ + (size_t)r * G.cap_succ, G.cap_succ, bm, sv, S.warp_sums))
-            block_sort_pairs(ek, ea, n, G.cap_events, sk, sv);
-        __syncthreads();
+        team_sort_pairs(T, ek, ea, n, G.cap_events, G.succ + (size_t)r * G.cap_succ, G.cap_succ, bm, sk, sv, S.warp_sums);
         TS(8);   // event sort
-        const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
-        const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
+        // every thread of the team owns `per` consecutive events: compose them, scan the composed maps inside the CTA,
+        // and (wide) chain the CTAs' totals through RepCtr::wide_mp
+        const uint32_t per = (n + T.nth - 1) / T.nth;
+        const uint32_t lo = min(n, T.tid * per), hi = min(n, lo + per);
         MP fb; fb.a = 0; fb.b = NEG_INF; MP fi = fb;
         for (uint32_t i = lo; i < hi; i++) { int type = (int)(ek[i] & 3ull); fb = mp_compose(fb, mp_bed(type)); fi = mp_compose(fi, mp_icu(type)); }
         s_bed[tid] = fb; s_icu[tid] = fi;
@@ -515,9 +652,26 @@ __device__ void post_body(const Eng &G, const int r, SmemSmall &S) {
             if (has) { s_bed[tid] = mp_compose(pb, s_bed[tid]); s_icu[tid] = mp_compose(pi, s_icu[tid]); }
             __syncthreads();
         }
-        const int beds0 = c->avail_beds, icu0 = c->avail_icu;
-        int beds = tid > 0 ? mp_apply(s_bed[tid - 1], beds0) : beds0;
-        int icu = tid > 0 ? mp_apply(s_icu[tid - 1], icu0) : icu0;
+        MP idm; idm.a = 0; idm.b = NEG_INF;
+        if (T.ncta > 1) {
+            if (tid == 0) {
+                const MP tb = s_bed[blockDim.x - 1], ti = s_icu[blockDim.x - 1];
+                c->wide_mp[T.cta][0] = tb.a; c->wide_mp[T.cta][1] = tb.b; c->wide_mp[T.cta][2] = ti.a; c->wide_mp[T.cta][3] = ti.b;
+            }
+            team_sync(T);
+            if (tid == 0) {
+                MP pb = idm, pi = idm;
+                for (uint32_t k = 0; k < T.cta; k++) {
+                    MP tb, ti; tb.a = c->wide_mp[k][0]; tb.b = c->wide_mp[k][1]; ti.a = c->wide_mp[k][2]; ti.b = c->wide_mp[k][3];
+                    pb = mp_compose(pb, tb); pi = mp_compose(pi, ti);
+                }
+                S.pre_bed = pb; S.pre_icu = pi;
+            }
+            __syncthreads();
+        } else if (tid == 0) { S.pre_bed = idm; S.pre_icu = idm; }
+        __syncthreads();
+        int beds = mp_apply(tid > 0 ? mp_compose(S.pre_bed, s_bed[tid - 1]) : S.pre_bed, beds0);
+        int icu = mp_apply(tid > 0 ? mp_compose(S.pre_icu, s_icu[tid - 1]) : S.pre_icu, icu0);
         for (uint32_t i = lo; i < hi; i++) {
             int type = (int)(ek[i] & 3ull);
             int32_t a = ea[i];
@@ -560,27 +714,53 @@ __device__ void post_body(const Eng &G, const int r, SmemSmall &S) {
             beds = mp_apply(mp_bed(type), beds);
             icu = mp_apply(mp_icu(type), icu);
         }
-        __syncthreads();
-        if (tid == 0) { c->avail_beds = mp_apply(s_bed[blockDim.x - 1], beds0); c->avail_icu = mp_apply(s_icu[blockDim.x - 1], icu0); }
+        // the last thread of the team has composed everything before it; its running counters are the day's result
+        if (T.tid == T.nth - 1) { c->avail_beds = beds; c->avail_icu = icu; }
     }
-    __syncthreads();
+    team_sync(T);
     TS(9);   // capacity scan + outcomes
-    if (tid == 0) {
+    if (T.tid == 0) {
         c->qsel ^= 1u;
-        c->n_queue = min(c->n_newq, G.cap_queue);
+        c->n_queue = min(n_newq, G.cap_queue);
         c->n_newq = 0;
         c->day = day + 1;            // main.pyx:2009
     }
 }
 
-__global__ void __launch_bounds__(PRE_THREADS) k_pre(Eng G) { __shared__ SmemSmall S; pre_body(G, blockIdx.x + G.r0, S); }
-__global__ void __launch_bounds__(PRE_THREADS) k_post(Eng G) { __shared__ SmemSmall S; post_body(G, blockIdx.x + G.r0, S); }
-// end of day d (capacity scan) fused with the start of day d+1 (stats row, queue, tracing, ...): one launch less per day
-__global__ void __launch_bounds__(PRE_THREADS) k_between(Eng G) {
+// Narrow launch: grid = replicas.  Wide launch (cooperative): grid = (CTAs per replica, replicas); on a quiet day
+// only the lead CTA stays.  k_pre decides from the queue it is about to drain (nothing in k_pre changes n_queue).
+template <bool WIDE> __device__ __forceinline__ bool boundary_team(const Eng &G, int &r, Team &T, bool from_queue) {
+    if (!WIDE) { r = blockIdx.x + G.r0; T = team_of(&G.ctr[r], 0, 1); return true; }
+    r = blockIdx.y + G.r0;
+    RepCtr *c = &G.ctr[r];
+    const bool wide = from_queue ? c->n_queue >= (uint32_t)G.wide_min : c->wide_day != 0u;
+    if (!wide && blockIdx.x != 0) return false;
+    T = team_of(c, blockIdx.x, wide ? gridDim.x : 1);
+    return true;
+}
+template <bool WIDE> __global__ void __launch_bounds__(PRE_THREADS) k_pre(Eng G) {
     __shared__ SmemSmall S;
-    post_body(G, blockIdx.x + G.r0, S);
-    __syncthreads();
-    pre_body(G, blockIdx.x + G.r0, S);
+    int r; Team T;
+    if (!boundary_team<WIDE>(G, r, T, true)) return;
+    pre_body(G, r, S, T);
+    team_finish(T);
+}
+template <bool WIDE> __global__ void __launch_bounds__(PRE_THREADS) k_post(Eng G) {
+    __shared__ SmemSmall S;
+    int r; Team T;
+    if (!boundary_team<WIDE>(G, r, T, false)) return;
+    post_body(G, r, S, T);
+    team_finish(T);
+}
+// end of day d (capacity scan) fused with the start of day d+1 (stats row, queue, tracing, ...): one launch less per day
+template <bool WIDE> __global__ void __launch_bounds__(PRE_THREADS) k_between(Eng G) {
+    __shared__ SmemSmall S;
+    int r; Team T;
+    if (!boundary_team<WIDE>(G, r, T, false)) return;
+    post_body(G, r, S, T);
+    team_sync(T);
+    pre_body(G, r, S, T);
+    team_finish(T);
 }
 
 #endif

@@ -165,6 +165,9 @@ __global__ void __launch_bounds__(256) k_resolve(Eng G) {
         device_infect(G, r, c, (int32_t)at.cand, (int32_t)at.parent, src_h, 0, (int)(at.key & 127ull), false);
         G.rec[base + at.cand].winner = KEY_IDLE;
     }
+    // verdict for the day boundary that follows: enough capacity events or queued tests to be worth a team of CTAs
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        c->wide_day = (c->n_events >= (uint32_t)G.wide_min || c->n_newq >= (uint32_t)G.wide_min) ? 1u : 0u;
     if (DRAIN) {
         const uint32_t nq = min(c->n_newq, G.cap_queue);
         const int32_t *qa = G.q_agent + ((size_t)r * 2 + (c->qsel ^ 1u)) * G.cap_queue;

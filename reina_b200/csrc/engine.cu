@@ -59,6 +59,7 @@ struct rb_engine {
     // replica groups: the ensemble is split into n_groups sets of replicas, each advanced by its own chain of launches
     // on its own stream with a grid sized for its share of the SMs.  The groups run half a day apart, so the
     // latency-bound phases of one (k_resolve, the single-CTA day boundary) overlap the sweep / contact kernels of another.
+    int wide_ctas;                      // CTAs per replica of the wide day boundary (<= 1: one CTA per replica)
     int n_groups;
     ReplicaGroup grp[MAX_GROUPS];
     cudaEvent_t ev_fork;
@@ -166,7 +167,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     if (const char *s = getenv("RB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(s));   // measurement aid
     rb_engine *e = new rb_engine();
     e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0; e->have_graphs = false; e->comm = nullptr; e->merge_blocks = 1;
-    e->has_ipc = false; e->n_groups = 1;
+    e->has_ipc = false; e->n_groups = 1; e->wide_ctas = 1;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     Eng &G = e->G;
@@ -246,6 +247,15 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     if (setup_groups(e, sms)) { rb_destroy(e); return 1; }
+    // wide day boundary: only without replica groups (two wide launches on concurrent streams could each hold half
+    // the SMs and wait for the other), one CTA per SM at most
+    e->wide_ctas = 1;
+    // measured at 5 x 10^7 agents, one replica (ms per 180 days): 1 CTA 80.1; 16 CTAs 50.7; 32: 51.8; 64: 56.7 (the grid
+    // barrier grows with the team); threshold 2048 / 8192 / 32768 entries: 47.4 / 56.7 / 59.9
+    G.wide_min = 2048;
+    if (e->n_groups == 1 && R * 4 <= sms) { e->wide_ctas = 16; while (e->wide_ctas * R > sms) e->wide_ctas >>= 1; }     // a power of two (team sort)
+    if (const char *s = getenv("RB_WIDE_CTAS")) { int v = atoi(s); if (v >= 1 && v <= WIDE_MAX_CTAS && v * R <= sms) e->wide_ctas = v; }
+    if (const char *s = getenv("RB_WIDE_MIN")) G.wide_min = atoi(s);     // 0: every day is a wide day (tests)
     *out = e;
     return 0;
 }
@@ -368,13 +378,32 @@ extern "C" int rb_set_schedule(rb_engine *e, int32_t day0, int32_t n, const rb_d
     return 0;
 }
 
+// The day boundary: one CTA per replica, or -- few replicas of a large population -- a cooperative launch of
+// wide_ctas co-resident CTAs per replica (boundary.cuh, Team).  kind: 0 = k_pre, 1 = k_post, 2 = k_between.
+static void launch_boundary(rb_engine *e, int kind, int R, cudaStream_t st, const Eng &G) {
+    if (e->wide_ctas <= 1) {
+        if (kind == 0) k_pre<false><<<R, PRE_THREADS, 0, st>>>(G);
+        else if (kind == 1) k_post<false><<<R, PRE_THREADS, 0, st>>>(G);
+        else k_between<false><<<R, PRE_THREADS, 0, st>>>(G);
+        return;
+    }
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(e->wide_ctas, R); cfg.blockDim = dim3(PRE_THREADS); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;     // all CTAs co-resident: the team's grid barrier needs it
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (kind == 0) cudaLaunchKernelEx(&cfg, k_pre<true>, G);
+    else if (kind == 1) cudaLaunchKernelEx(&cfg, k_post<true>, G);
+    else cudaLaunchKernelEx(&cfg, k_between<true>, G);
+}
+
 // One "segment" = the grid kernels of day d followed by the fused day boundary d -> d+1.
 static void launch_segment(rb_engine *e, cudaStream_t st) {
     const Eng &G = e->G;
     k_sweep<<<dim3(e->sweep_blocks, G.R), SW_THREADS, 0, st>>>(G);
     k_expose<<<dim3(e->list_blocks, G.R), EX_THREADS, 0, st>>>(G);
     k_resolve<true><<<dim3(e->resolve_blocks, G.R), 256, 0, st>>>(G);
-    k_between<<<G.R, PRE_THREADS, 0, st>>>(G);
+    launch_boundary(e, 2, G.R, st, G);
 }
 
 // No kernel takes the day as an argument (each replica carries its own day counter and reads the schedule from
@@ -385,7 +414,7 @@ static void launch_group_segment(rb_engine *e, const ReplicaGroup &q, bool stagg
     k_expose<<<dim3(q.list_blocks, q.R), EX_THREADS, 0, q.stream>>>(G);
     if (stagger_mark) cudaEventRecord(q.ev_stagger, q.stream);       // the next group starts its day here
     k_resolve<true><<<dim3(q.resolve_blocks, q.R), 256, 0, q.stream>>>(G);
-    k_between<<<q.R, PRE_THREADS, 0, q.stream>>>(G);
+    launch_boundary(e, 2, q.R, q.stream, G);
 }
 
 #define GRAPH_DAYS 16
@@ -469,8 +498,8 @@ static int launch_day_sharded(rb_engine *e, bool last) {
     k_expose<<<dim3(e->list_blocks, 1), EX_THREADS, 0, st>>>(G);
     NK(g_nccl.AllGather(G.xbuf + (size_t)G.rank * G.xslot, G.xbuf, G.xslot, ncclChar, e->comm, st));
     k_merge<<<e->merge_blocks, 256, 0, st>>>(G);
-    if (last) { k_resolve<false><<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G); k_post<<<1, PRE_THREADS, 0, st>>>(G); }
-    else { k_resolve<true><<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G); k_between<<<1, PRE_THREADS, 0, st>>>(G); }
+    if (last) { k_resolve<false><<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G); launch_boundary(e, 1, 1, st, G); }
+    else { k_resolve<true><<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G); launch_boundary(e, 2, 1, st, G); }
     e->launches += 5;
     return 0;
 }
@@ -488,7 +517,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     const int R = G.R;
     if (e->comm) {
         CK(cudaEventRecord(e->ev0, e->stream));
-        k_pre<<<1, PRE_THREADS, 0, e->stream>>>(G); e->launches++;
+        launch_boundary(e, 0, 1, e->stream, G); e->launches++;
         for (int d = 0; d < n_days; d++) if (launch_day_sharded(e, d == n_days - 1)) return 1;
         CK(cudaEventRecord(e->ev1, e->stream));
         CK(cudaGetLastError());
@@ -497,7 +526,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     }
     if (e->n_groups > 1) {
         CK(cudaEventRecord(e->ev0, e->stream));
-        k_pre<<<R, PRE_THREADS, 0, e->stream>>>(G); e->launches++;
+        launch_boundary(e, 0, R, e->stream, G); e->launches++;
         CK(cudaEventRecord(e->ev_fork, e->stream));
         for (int g = 0; g < e->n_groups; g++) {
             ReplicaGroup &q = e->grp[g];
@@ -511,7 +540,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
             k_sweep<<<dim3(q.sweep_blocks, q.R), SW_THREADS, 0, q.stream>>>(Gq);
             k_expose<<<dim3(q.list_blocks, q.R), EX_THREADS, 0, q.stream>>>(Gq);
             k_resolve<false><<<dim3(q.resolve_blocks, q.R), 256, 0, q.stream>>>(Gq);
-            k_post<<<q.R, PRE_THREADS, 0, q.stream>>>(Gq);
+            launch_boundary(e, 1, q.R, q.stream, Gq);
             e->launches += 4;
             CK(cudaEventRecord(q.ev_join, q.stream));
             CK(cudaStreamWaitEvent(e->stream, q.ev_join, 0));
@@ -522,14 +551,14 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
         return 0;
     }
     CK(cudaEventRecord(e->ev0, e->stream));
-    k_pre<<<R, PRE_THREADS, 0, e->stream>>>(G); e->launches++;
+    launch_boundary(e, 0, R, e->stream, G); e->launches++;
     int mid = n_days - 1;
     while (mid >= GRAPH_DAYS) { CK(cudaGraphLaunch(e->graph[0], e->stream)); mid -= GRAPH_DAYS; e->launches += 4 * GRAPH_DAYS; }
     while (mid > 0) { CK(cudaGraphLaunch(e->graph[1], e->stream)); mid -= 1; e->launches += 4; }
     k_sweep<<<dim3(e->sweep_blocks, R), SW_THREADS, 0, e->stream>>>(G);
     k_expose<<<dim3(e->list_blocks, R), EX_THREADS, 0, e->stream>>>(G);
     k_resolve<false><<<dim3(e->resolve_blocks, R), 256, 0, e->stream>>>(G);
-    k_post<<<R, PRE_THREADS, 0, e->stream>>>(G);
+    launch_boundary(e, 1, R, e->stream, G);
     e->launches += 4;
     CK(cudaEventRecord(e->ev1, e->stream));
     CK(cudaGetLastError());
@@ -548,11 +577,11 @@ extern "C" int rb_step_profiled(rb_engine *e, int32_t n_days, float *ms_per_kern
     for (int d = 0; d < n_days; d++) {
         cudaEvent_t *v = &ev[(size_t)d * 6];
         CK(cudaEventRecord(v[0], e->stream));
-        k_pre<<<R, PRE_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[1], e->stream));
+        launch_boundary(e, 0, R, e->stream, G); CK(cudaEventRecord(v[1], e->stream));
         k_sweep<<<dim3(e->sweep_blocks, R), SW_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[2], e->stream));
         k_expose<<<dim3(e->list_blocks, R), EX_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[3], e->stream));
         k_resolve<false><<<dim3(e->resolve_blocks, R), 256, 0, e->stream>>>(G); CK(cudaEventRecord(v[4], e->stream));
-        k_post<<<R, PRE_THREADS, 0, e->stream>>>(G); CK(cudaEventRecord(v[5], e->stream));
+        launch_boundary(e, 1, R, e->stream, G); CK(cudaEventRecord(v[5], e->stream));
         e->launches += 5;
     }
     CK(cudaGetLastError());

@@ -48,6 +48,7 @@
 
 enum { EV_HOSP_CLAIM = 0, EV_WARD_RELEASE = 1, EV_TO_ICU = 2, EV_ICU_RELEASE = 3 };
 
+#define WIDE_MAX_CTAS 64      // CTAs of one replica's wide day boundary
 #define SORT_SMEM 2048
 #ifndef PRE_THREADS
 #define PRE_THREADS 512       // day-boundary CTA: two fit on an SM, so 256 replicas are one wave
@@ -115,6 +116,10 @@ struct RepCtr {
     alignas(128) int32_t drain_det[RB_MAX_AGES];  // detections of an early queue drain, per age, booked at the next day boundary
     alignas(128) uint32_t n_l0;
     uint32_t n_l1, n_edges;
+    // wide day boundary (boundary.cuh, Team): grid barrier word on its own line, today's verdict, per-CTA scan totals
+    alignas(128) unsigned int wide_bar;
+    alignas(128) uint32_t wide_day;
+    int32_t wide_mp[WIDE_MAX_CTAS][4];
     long long dbg_t[16];                          // measurement aid: cycles spent per phase of the day-boundary kernel
     long long dbg_last;
 };
@@ -144,6 +149,7 @@ struct Eng {
     // population-sharded mode (rb_shard_init): every rank holds the whole state, sweeps and exposes only the agents
     // it owns, and publishes what the others must know in its slot of the exchange buffer (one all-gather per day)
     int32_t rank, nranks;
+    int32_t wide_min;                              // a day with this many capacity events / queued tests gets the wide boundary
     int32_t r0;                                    // first replica of this launch (replica groups on concurrent streams, engine.cu)
     uint8_t *xbuf; size_t xslot;                   // [nranks] message slots; slot `rank` is written locally
     uint32_t xcap_q, xcap_ev, xcap_upd, xcap_succ;

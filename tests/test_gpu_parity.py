@@ -68,6 +68,49 @@ def test_contact_tracing_scenario(cuda_lib, oracle_lib):
     _run_and_compare(gpu, cpu, 180)
 
 
+@pytest.fixture
+def wide_boundary(monkeypatch):
+    """Every day boundary runs as a TEAM of CTAs joined by a grid barrier (boundary.cuh), whatever the day's load:
+    the engine reads RB_WIDE_MIN / RB_WIDE_CTAS when it is created."""
+    monkeypatch.setenv('RB_WIDE_MIN', '0')
+    monkeypatch.setenv('RB_WIDE_CTAS', '8')
+
+
+@pytest.mark.parametrize('case', ['stress', 'tracing', 'default', 'replicas'])
+def test_wide_day_boundary(cuda_lib, oracle_lib, wide_boundary, case):
+    """The multi-CTA day boundary (team sort, chained capacity scan, tracing over the whole team) against the oracle:
+    every intervention type with a saturated tiny hospital, the contact-tracing scenario, the default run, and
+    three replicas side by side."""
+    v = helpers.inputs.default_variables()
+    if case == 'stress':
+        counts = helpers.small_population(80000)
+        v['hospital_beds'], v['icu_units'] = 25, 3
+        gpu, cpu = _pair(cuda_lib, oracle_lib, variables=v, age_count_override=counts, seed=11, interventions=helpers.stress_interventions())
+        _run_and_compare(gpu, cpu, 120, chunk=7)
+    elif case == 'tracing':
+        counts = helpers.small_population(150000)
+        v['hospital_beds'], v['icu_units'] = helpers.scaled_capacity(150000)
+        gpu, cpu = _pair(cuda_lib, oracle_lib, variables=v, age_count_override=counts, seed=5, scenario='hammer-and-dance')
+        _run_and_compare(gpu, cpu, 180)
+    elif case == 'default':
+        counts = helpers.small_population(120000)
+        v['hospital_beds'], v['icu_units'] = helpers.scaled_capacity(120000)
+        gpu, cpu = _pair(cuda_lib, oracle_lib, variables=v, age_count_override=counts, seed=2)
+        _run_and_compare(gpu, cpu, 180)
+    else:
+        counts = helpers.small_population(30000)
+        v['hospital_beds'], v['icu_units'] = helpers.scaled_capacity(30000)
+        kw = dict(variables=v, age_count_override=counts, interventions=helpers.stress_interventions())
+        gpu = helpers.make_context(cuda_lib, seed=40, n_replicas=3, **kw)
+        gpu.run(100)
+        rows = gpu.series(0, 100)
+        for r in range(3):
+            cpu = helpers.make_context(oracle_lib, seed=40 + r, **kw)
+            cpu.run(100)
+            assert np.array_equal(rows[r], cpu.series(0, 100)[0]), 'replica %d differs' % r
+            assert np.array_equal(gpu._engine.read_agents(r), cpu._engine.read_agents(0))
+
+
 def test_replicas_match_single_runs(cuda_lib, oracle_lib):
     """An R-replica context equals R single-seed runs (replica r uses seed + r)."""
     counts = helpers.small_population(30000)

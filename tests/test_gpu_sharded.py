@@ -110,6 +110,24 @@ def test_world_size_1_message_path(case):
     _check_against_oracle(out, 1, case)
 
 
+@pytest.fixture
+def wide_boundary(monkeypatch):
+    """Force the multi-CTA day boundary on every day (the spawned rank processes inherit the environment)."""
+    monkeypatch.setenv('RB_WIDE_MIN', '0')
+    monkeypatch.setenv('RB_WIDE_CTAS', '10')
+
+
+@pytest.mark.parametrize('case', ['stress', 'tracing'])
+def test_world_size_1_wide_boundary(wide_boundary, case):
+    out = _run_sharded(1, case, chunk=50)
+    _check_against_oracle(out, 1, case)
+
+
+def test_two_ranks_wide_boundary(wide_boundary):
+    out = _run_sharded(2, 'stress', chunk=31)
+    _check_against_oracle(out, 2, 'stress')
+
+
 @pytest.mark.parametrize('case', ['stress', 'default', 'tracing'])
 def test_two_ranks_equal_oracle(case):
     out = _run_sharded(2, case, chunk=31)

@@ -19,6 +19,7 @@ ap.add_argument('--agents', type=float, default=50e6)
 ap.add_argument('--days', type=int, default=180)
 ap.add_argument('--steps', type=int, default=3)
 ap.add_argument('--warmup', type=int, default=1)
+ap.add_argument('--force-shard', action='store_true', help='world size 1 through the message / merge path (profiling aid)')
 a = ap.parse_args()
 rank, world, local = sharded.world()
 
@@ -41,7 +42,7 @@ for iv in v['interventions']:
 v['interventions'] = ivs
 args = inputs.build_context_args(v, age_count_override=inputs.synthetic_age_counts(n))
 args['random_seed'] = 0
-spec = sharded.shard_spec(dist if world > 1 else None) if world > 1 else None
+spec = sharded.shard_spec(dist if world > 1 else None) if (world > 1 or a.force_shard) else None
 ctx = model.Context(n_replicas=1, device=local, max_days=a.days + 1, shard=spec, **args)
 for iv in inputs.active_interventions(v):
     ctx.add_intervention(iv)

@@ -17,7 +17,7 @@ lib = ctx._engine.lib.dll
 lib.rb_debug_flag.argtypes = [ctypes.c_void_p, ctypes.c_int32]
 lib.rb_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
 lib.rb_debug_flag(ctx._engine.h, 9)
-names = {0: 'stats row', 1: 'imports+init_day', 2: 'queue drain', 3: 'contact tracing', 4: 'vaccination', 8: 'event sort', 9: 'capacity scan'}
+names = {0: 'stats row', 1: 'imports+init_day', 10: 'queue sort', 2: 'queue drain', 5: 'trace l0', 6: 'trace l1+edges', 7: 'trace cycles', 3: 'trace finish', 4: 'vaccination', 8: 'event sort', 9: 'capacity scan'}
 prev = np.zeros(16, dtype=np.int64)
 G = len(ctx.age_group_labels)
 for lo in range(0, days, stretch):
