@@ -194,9 +194,13 @@ int rb_step_profiled(rb_engine *e, int32_t n_days, float *ms_per_kernel);
  * rank 0 obtains a 128-byte NCCL unique id with rb_shard_unique_id and hands it to the others by any means; each rank
  * calls rb_shard_init(e, rank, nranks, id, exchange_capacity) before the first rb_step.  Agents are dealt to the ranks in
  * stripes of 4096 (age-sorted order, so every rank holds ~1/nranks of every age).  A rank sweeps and samples contacts only
- * for the agents it owns; once per simulated day the ranks all-gather (NCCL) their day's cross-shard events -- successful
+ * for the agents it owns; once per simulated day the ranks exchange their day's cross-shard events -- successful
  * transmissions, state changes, test-queue entries, capacity events, counter deltas -- and every rank applies all of them,
  * so counters, queues and every rb_read_* result are identical on all ranks and bit-identical to a single-GPU run.
+ * The exchange runs over NVLink peer memory: every rank maps every other rank's message buffer (CUDA IPC, set up through
+ * the NCCL communicator), publishes a per-day flag when its message is complete, and the merge kernel pulls exactly the
+ * bytes each message holds.  Where peer mapping is not possible (ranks inside one process, no peer access, or
+ * RB_SHARD_EXCHANGE=nccl) the fixed-size message slots travel through one ncclAllGather per day instead.
  * Per-agent day counters and severity are authoritative on the owning rank only (rb_read_agents: take agent a from rank
  * (a >> 12) % nranks).  exchange_capacity scales the per-day message capacity (0 = default); overflow sets RB_OTHER_FAILURE.
  * libnccl.so.2 is loaded at run time by these calls only. */
@@ -204,7 +208,8 @@ int rb_shard_unique_id(uint8_t *out128);
 int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const uint8_t *unique_id128, float exchange_capacity);
 int32_t rb_shard_rank(rb_engine *e);
 int32_t rb_shard_nranks(rb_engine *e);
-int64_t rb_shard_message_bytes(rb_engine *e);   /* bytes each rank contributes to the daily all-gather */
+int64_t rb_shard_message_bytes(rb_engine *e);   /* capacity of one rank's daily message (what the all-gather path moves) */
+int32_t rb_shard_exchange(rb_engine *e);        /* 0 = not sharded, 1 = ncclAllGather, 2 = NVLink peer memory */
 
 /* ---- Checkpoint / resume (the reference keeps its state only in process memory).
  * The blob holds the whole mutable state between two rb_step calls (packed words, agent records, bitmaps, counters, test

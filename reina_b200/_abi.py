@@ -88,7 +88,7 @@ SYMBOLS = ['create', 'destroy', 'reset', 'set_initial_state', 'step_profiled', '
 
 
 # population-sharded mode: exported by the CUDA library only (the sequential CPU oracle has no ranks)
-SHARD_SYMBOLS = ['shard_unique_id', 'shard_init', 'shard_rank', 'shard_nranks', 'shard_message_bytes',
+SHARD_SYMBOLS = ['shard_unique_id', 'shard_init', 'shard_rank', 'shard_nranks', 'shard_message_bytes', 'shard_exchange',
                  # checkpoint / resume of the device-resident state
                  'state_bytes', 'save_state', 'load_state']
 SH_SHIFT = 12      # ownership stripes of 4096 agents, dealt round-robin over the ranks (engine.cu owns())
@@ -164,6 +164,7 @@ class Library:
             f['shard_nranks'].argtypes = [vp]
             f['shard_message_bytes'].argtypes = [vp]
             f['shard_message_bytes'].restype = C.c_int64
+            f['shard_exchange'].argtypes = [vp]
             f['state_bytes'].argtypes = [vp]
             f['state_bytes'].restype = C.c_int64
             f['save_state'].argtypes = [vp, C.c_void_p, C.c_int64]

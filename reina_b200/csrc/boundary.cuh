@@ -597,7 +597,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S, Team &T) {
         c->n_q_base = c->n_newq;
     }
     if (G.xbuf) {     // this rank's message header: the sweep and the contact kernel add to it from zero
-        uint32_t *hw = (uint32_t *)xslot_of(G, G.rank).hdr;
+        uint32_t *hw = (uint32_t *)xslot_of(G, G.rank, day).hdr;
         for (uint32_t i = T.tid; i < (uint32_t)(sizeof(RepCtr) / 4); i += T.nth) hw[i] = 0u;
     }
 }

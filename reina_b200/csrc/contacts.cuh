@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
     Attempt *succ = G.succ + (size_t)r * G.cap_succ;
     uint32_t cap_succ = G.cap_succ;
     RepCtr *cd = c;
-    if (G.xbuf) { const XSlot x = xslot_of(G, G.rank); succ = x.succ; cap_succ = G.xcap_succ; cd = x.hdr; }
+    if (G.xbuf) { const XSlot x = xslot_of(G, G.rank, c->day); succ = x.succ; cap_succ = G.xcap_succ; cd = x.hdr; }
     const uint32_t *sus = G.sus + (size_t)r * G.sus_words;
     const uint32_t day = (uint32_t)c->day;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

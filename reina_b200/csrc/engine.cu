@@ -64,6 +64,7 @@ struct rb_engine {
     ReplicaGroup grp[MAX_GROUPS];
     cudaEvent_t ev_fork;
     ncclComm_t comm;                    // population-sharded mode
+    int n_peer_open;                    // peer buffers mapped through CUDA IPC: ranks [0, n_peer_open) except the own one
     int merge_blocks;
     Ipc ipc; bool has_ipc;              // initial population condition, re-applied by rb_reset
 };
@@ -145,6 +146,7 @@ extern "C" void rb_destroy(rb_engine *e) {
         cudaStreamDestroy(e->grp[g].stream); cudaEventDestroy(e->grp[g].ev_stagger); cudaEventDestroy(e->grp[g].ev_join);
     }
     if (e->n_groups > 1) cudaEventDestroy(e->ev_fork);
+    for (int k = 0; k < e->n_peer_open; k++) if (k != e->G.rank && e->G.xpeer[k]) cudaIpcCloseMemHandle(e->G.xpeer[k]);
     if (e->comm) g_nccl.CommDestroy(e->comm);
     for (void *p : e->allocs) cudaFree(p);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
@@ -167,7 +169,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     if (const char *s = getenv("RB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(s));   // measurement aid
     rb_engine *e = new rb_engine();
     e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0; e->have_graphs = false; e->comm = nullptr; e->merge_blocks = 1;
-    e->has_ipc = false; e->n_groups = 1; e->wide_ctas = 1;
+    e->has_ipc = false; e->n_groups = 1; e->wide_ctas = 1; e->n_peer_open = 0;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     Eng &G = e->G;
@@ -298,6 +300,7 @@ extern "C" int rb_reset(rb_engine *e, uint32_t seed) {
     CK(cudaStreamSynchronize(e->stream));
     e->cfg.seed = seed;
     e->day = 0;
+    e->G.xepoch++;
     if (init_counters(e, seed)) return 1;
     k_init<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G); e->launches++;
     if (e->has_ipc) { k_initial_state<<<e->G.R, 32, 0, e->stream>>>(e->G, e->ipc); e->launches++; }
@@ -475,9 +478,58 @@ extern "C" int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const u
     G.xcap_q = (uint32_t)(share / 256) + 2048;
     G.xcap_ev = (uint32_t)(share / 512) + 2048;
     G.xslot = xslot_bytes(G.xcap_q, G.xcap_ev, G.xcap_upd, G.xcap_succ);
-    if (dalloc(e, &G.xbuf, G.xslot * nranks)) return 1;
-    CK(cudaMemset(G.xbuf, 0, G.xslot * nranks));
     G.rank = rank; G.nranks = nranks;
+    // Exchange through peer memory when every rank can map every other rank's buffer (CUDA IPC; one process per GPU on
+    // one NVLink box), else -- ranks in one process, no peer access, RB_SHARD_EXCHANGE=nccl -- through ncclAllGather.
+    {
+        const char *mode = getenv("RB_SHARD_EXCHANGE");
+        int ok = !(mode && strcmp(mode, "nccl") == 0);
+        const size_t own_bytes = XFLAG_BYTES + 2 * G.xslot;
+        uint8_t *own = nullptr;
+        struct Hello { cudaIpcMemHandle_t h; int32_t ok; int32_t pad[15]; };
+        static_assert(sizeof(Hello) == 128, "Hello is one 128-byte record");
+        std::vector<Hello> all(nranks);
+        Hello *d_all = nullptr;
+        if (dalloc(e, &d_all, (size_t)nranks)) return 1;
+        if (ok && cudaMalloc((void **)&own, own_bytes) != cudaSuccess) { cudaGetLastError(); ok = 0; own = nullptr; }
+        Hello me; memset(&me, 0, sizeof me);
+        if (ok && nranks > 1 && cudaIpcGetMemHandle(&me.h, own) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        me.ok = ok;
+        auto gather = [&]() -> int {       // everybody learns everybody's record
+            CK(cudaMemcpy(d_all + rank, &me, sizeof me, cudaMemcpyHostToDevice));
+            NK(g_nccl.AllGather(d_all + rank, d_all, sizeof(Hello), ncclChar, e->comm, e->stream));
+            CK(cudaStreamSynchronize(e->stream));
+            CK(cudaMemcpy(all.data(), d_all, sizeof(Hello) * nranks, cudaMemcpyDeviceToHost));
+            return 0;
+        };
+        if (gather()) return 1;
+        for (int k = 0; k < nranks; k++) ok = ok && all[k].ok;
+        if (ok) {
+            for (int k = 0; k < nranks; k++) {
+                if (k == rank) { G.xpeer[k] = own; continue; }
+                void *q = nullptr;
+                if (cudaIpcOpenMemHandle(&q, all[k].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+                G.xpeer[k] = (uint8_t *)q; e->n_peer_open = k + 1;
+            }
+            me.ok = ok;
+            if (gather()) return 1;        // second round: did every rank open every handle?
+            for (int k = 0; k < nranks; k++) ok = ok && all[k].ok;
+        }
+        if (ok) {
+            e->allocs.push_back(own);
+            CK(cudaMemset(own, 0, own_bytes));
+            G.xbuf = own; G.xp2p = 1; G.xepoch = 1;
+            // nobody may publish before every rank has cleared its flag line
+            if (gather()) return 1;
+        } else {
+            for (int k = 0; k < e->n_peer_open; k++) if (k != rank && G.xpeer[k]) cudaIpcCloseMemHandle(G.xpeer[k]);
+            e->n_peer_open = 0; memset(G.xpeer, 0, sizeof G.xpeer);
+            if (own) cudaFree(own);
+            G.xp2p = 0;
+            if (dalloc(e, &G.xbuf, G.xslot * nranks)) return 1;
+            CK(cudaMemset(G.xbuf, 0, G.xslot * nranks));
+        }
+    }
     int sb = (e->sweep_blocks + nranks - 1) / nranks; if (sb < 1) sb = 1;
     e->sweep_blocks = sb;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, e->cfg.device));
@@ -488,6 +540,7 @@ extern "C" int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const u
 extern "C" int32_t rb_shard_rank(rb_engine *e) { return e->G.rank; }
 extern "C" int32_t rb_shard_nranks(rb_engine *e) { return e->G.nranks; }
 extern "C" int64_t rb_shard_message_bytes(rb_engine *e) { return e->comm ? (int64_t)e->G.xslot : 0; }
+extern "C" int32_t rb_shard_exchange(rb_engine *e) { return !e->comm ? 0 : (e->G.xp2p ? 2 : 1); }
 
 // One simulated day in sharded mode: sweep and contacts over the owned stripes, ONE all-gather of the ranks' messages,
 // then merge / resolve / day boundary replicated on every rank.
@@ -496,7 +549,8 @@ static int launch_day_sharded(rb_engine *e, bool last) {
     cudaStream_t st = e->stream;
     k_sweep<<<dim3(e->sweep_blocks, 1), SW_THREADS, 0, st>>>(G);
     k_expose<<<dim3(e->list_blocks, 1), EX_THREADS, 0, st>>>(G);
-    NK(g_nccl.AllGather(G.xbuf + (size_t)G.rank * G.xslot, G.xbuf, G.xslot, ncclChar, e->comm, st));
+    if (G.xp2p) k_publish<<<1, 32, 0, st>>>(G);
+    else NK(g_nccl.AllGather(G.xbuf + (size_t)G.rank * G.xslot, G.xbuf, G.xslot, ncclChar, e->comm, st));
     k_merge<<<e->merge_blocks, 256, 0, st>>>(G);
     if (last) { k_resolve<false><<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G); launch_boundary(e, 1, 1, st, G); }
     else { k_resolve<true><<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G); launch_boundary(e, 2, 1, st, G); }
@@ -771,5 +825,6 @@ extern "C" int rb_load_state(rb_engine *e, const void *in, int64_t n_bytes) {
     const uint8_t *o = (const uint8_t *)in + sizeof h;
     for (const StatePart &p : state_parts(e)) { CK(cudaMemcpy(p.dev, o, p.bytes, cudaMemcpyHostToDevice)); o += p.bytes; }
     e->day = h.day; e->cfg.seed = h.seed;
+    e->G.xepoch++;
     return 0;
 }

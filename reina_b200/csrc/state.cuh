@@ -48,6 +48,7 @@
 
 enum { EV_HOSP_CLAIM = 0, EV_WARD_RELEASE = 1, EV_TO_ICU = 2, EV_ICU_RELEASE = 3 };
 
+#define MAX_RANKS 16
 #define WIDE_MAX_CTAS 64      // CTAs of one replica's wide day boundary
 #define SORT_SMEM 2048
 #ifndef PRE_THREADS
@@ -151,12 +152,20 @@ struct Eng {
     int32_t rank, nranks;
     int32_t wide_min;                              // a day with this many capacity events / queued tests gets the wide boundary
     int32_t r0;                                    // first replica of this launch (replica groups on concurrent streams, engine.cu)
-    uint8_t *xbuf; size_t xslot;                   // [nranks] message slots; slot `rank` is written locally
+    // exchange through NCCL: xbuf = [nranks] message slots, slot `rank` written locally, the rest filled by the daily
+    // all-gather.  Exchange through peer memory (xp2p): every rank owns [256-byte flag line][slot of even days][slot of
+    // odd days], xpeer[k] is rank k's buffer mapped through CUDA IPC (xpeer[rank] = xbuf = the own one), and k_merge
+    // pulls exactly the bytes each message holds over NVLink once the owner's flag says the day is complete.
+    uint8_t *xbuf; size_t xslot;
+    uint8_t *xpeer[MAX_RANKS];
+    int32_t xp2p; uint32_t xepoch;                 // xepoch: bumped by every reset / state load, keeps the flags monotonic
     uint32_t xcap_q, xcap_ev, xcap_upd, xcap_succ;
 };
 
 // Ownership: stripes of 4096 agents (one warp step of the sweep) dealt round-robin, so every rank holds ~1/nranks of every age.
+#define XFLAG_BYTES 256
 #define SH_SHIFT 12
+__device__ __forceinline__ uint32_t xflag_value(const Eng &G, int day) { return G.xepoch * 65536u + (uint32_t)day + 1u; }
 __device__ __forceinline__ bool owns(const Eng &G, uint32_t a) { return G.nranks == 1 || (int)((a >> SH_SHIFT) % (uint32_t)G.nranks) == G.rank; }
 
 // One rank's message: a RepCtr used as the header (count deltas of the sweep, list lengths) followed by the lists.
@@ -171,8 +180,8 @@ __host__ __device__ inline size_t xalign(size_t x) { return (x + 255) & ~(size_t
 __host__ __device__ inline size_t xslot_bytes(uint32_t cq, uint32_t ce, uint32_t cu, uint32_t cs) {
     return xalign(sizeof(RepCtr)) + xalign(8ull * cq) + xalign(4ull * cq) + xalign(8ull * ce) + xalign(4ull * ce) + xalign(8ull * cu) + xalign(16ull * cs);
 }
-__device__ __forceinline__ XSlot xslot_of(const Eng &G, int rk) {
-    uint8_t *p = G.xbuf + (size_t)rk * G.xslot;
+__device__ __forceinline__ XSlot xslot_of(const Eng &G, int rk, int day) {
+    uint8_t *p = G.xp2p ? G.xpeer[rk] + XFLAG_BYTES + (size_t)(day & 1) * G.xslot : G.xbuf + (size_t)rk * G.xslot;
     XSlot s;
     s.hdr = (RepCtr *)p; p += xalign(sizeof(RepCtr));
     s.q_key = (unsigned long long *)p; p += xalign(8ull * G.xcap_q);

@@ -59,7 +59,7 @@ __device__ __forceinline__ SweepOut sweep_out(const Eng &G, int r, RepCtr *c) {
         O.ev_key = G.ev_key + (size_t)r * G.cap_events; O.ev_agent = G.ev_agent + (size_t)r * G.cap_events; O.cap_ev = G.cap_events;
         O.upd = nullptr; O.cap_upd = 0;
     } else {
-        const XSlot x = xslot_of(G, G.rank);
+        const XSlot x = xslot_of(G, G.rank, c->day);
         O.cd = x.hdr; O.q_key = x.q_key; O.q_agent = x.q_agent; O.cap_q = G.xcap_q;
         O.ev_key = x.ev_key; O.ev_agent = x.ev_agent; O.cap_ev = G.xcap_ev; O.upd = x.upd; O.cap_upd = G.xcap_upd;
     }
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
     uint2 *items = G.items + (size_t)r * G.cap_items;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpRings &W = s_rings[warp];
-    RepCtr *cd = !G.xbuf ? c : xslot_of(G, G.rank).hdr;      // counters the sweep adds to
+    RepCtr *cd = !G.xbuf ? c : xslot_of(G, G.rank, c->day).hdr;      // counters the sweep adds to
     const int nrk = G.nranks, rk = G.rank;
     const int stride = gridDim.x * SW_WARPS;
     const bool stream = c->stream_mode != 0;

@@ -48,7 +48,7 @@ def _worker(rank, world, uid, case, chunk, q):
         eng = ctx._engine
         q.put((rank, dict(series=ctx.series(0, days), agents=eng.read_agents(0), queue=np.sort(eng.read_queue(0)),
                           avail=eng.read_available(0), launches=eng.launch_count(),
-                          msg_bytes=eng.lib.f['shard_message_bytes'](eng.h))))
+                          msg_bytes=eng.lib.f['shard_message_bytes'](eng.h), exchange=eng.lib.f['shard_exchange'](eng.h))))
     except Exception:
         q.put((rank, traceback.format_exc()))
 
@@ -133,6 +133,15 @@ def test_two_ranks_equal_oracle(case):
     out = _run_sharded(2, case, chunk=31)
     _check_against_oracle(out, 2, case)
     assert out[0]['msg_bytes'] > 0
+    assert out[0]['exchange'] == out[1]['exchange'] == 2, 'expected the NVLink peer-memory exchange between two processes'
+
+
+def test_two_ranks_nccl_exchange(monkeypatch):
+    """The fallback exchange: fixed-size slots through one ncclAllGather per day."""
+    monkeypatch.setenv('RB_SHARD_EXCHANGE', 'nccl')
+    out = _run_sharded(2, 'stress', chunk=31)
+    _check_against_oracle(out, 2, 'stress')
+    assert out[0]['exchange'] == 1
 
 
 def test_four_ranks_equal_oracle():

@@ -71,7 +71,8 @@ if rank == 0:
                           unit='agent-days/s', n_gpus=world, agents=n, days=a.days, ms_per_run=m, steps=a.steps, warmup=a.warmup,
                           scaling='strong', all_infected_last_day=float(chk.item()),
                           ranks_agree=bool(lo.item() == hi.item()),
-                          message_bytes_per_rank_per_day=int(ctx._engine.lib.f['shard_message_bytes'](ctx._engine.h)) if world > 1 else 0)),
+                          message_bytes_per_rank_per_day=int(ctx._engine.lib.f['shard_message_bytes'](ctx._engine.h)) if world > 1 else 0,
+                          exchange={0: 'none', 1: 'ncclAllGather', 2: 'NVLink peer memory'}[int(ctx._engine.lib.f['shard_exchange'](ctx._engine.h))])),
           flush=True)
 if world > 1:
     dist.barrier()
