@@ -64,6 +64,7 @@ struct rb_engine {
     ReplicaGroup grp[MAX_GROUPS];
     cudaEvent_t ev_fork;
     ncclComm_t comm;                    // population-sharded mode
+    bool shard_timing; std::vector<cudaEvent_t> shard_events;
     int n_peer_open;                    // peer buffers mapped through CUDA IPC: ranks [0, n_peer_open) except the own one
     int merge_blocks;
     Ipc ipc; bool has_ipc;              // initial population condition, re-applied by rb_reset
@@ -169,7 +170,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     if (const char *s = getenv("RB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(s));   // measurement aid
     rb_engine *e = new rb_engine();
     e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0; e->have_graphs = false; e->comm = nullptr; e->merge_blocks = 1;
-    e->has_ipc = false; e->n_groups = 1; e->wide_ctas = 1; e->n_peer_open = 0;
+    e->has_ipc = false; e->n_groups = 1; e->wide_ctas = 1; e->n_peer_open = 0; e->shard_timing = getenv("RB_SHARD_TIMING") != nullptr;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     Eng &G = e->G;
@@ -530,10 +531,13 @@ extern "C" int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const u
             CK(cudaMemset(G.xbuf, 0, G.xslot * nranks));
         }
     }
-    int sb = (e->sweep_blocks + nranks - 1) / nranks; if (sb < 1) sb = 1;
-    e->sweep_blocks = sb;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, e->cfg.device));
-    e->merge_blocks = prop.multiProcessorCount * 2;
+    {   // a rank walks 1 / nranks of the activity bitmap, with the whole GPU: one wave unless there are fewer warp steps than that
+        const int want = ((G.sus_words / 4 + 31) / 32 + nranks - 1) / nranks;           // this rank's warp steps
+        int sb = (want + SW_WARPS - 1) / SW_WARPS; if (sb < 1) sb = 1;
+        if (sb < e->sweep_blocks) e->sweep_blocks = sb;
+    }
+    e->merge_blocks = prop.multiProcessorCount * 8 / nranks * nranks;      // a multiple of nranks: k_merge deals its blocks to the ranks
     return 0;
 }
 
@@ -547,14 +551,23 @@ extern "C" int32_t rb_shard_exchange(rb_engine *e) { return !e->comm ? 0 : (e->G
 static int launch_day_sharded(rb_engine *e, bool last) {
     const Eng &G = e->G;
     cudaStream_t st = e->stream;
+    // RB_SHARD_TIMING (measurement aid): device time per phase, summed over the days of the step, printed by rb_sync
+    auto mark = [&]() { if (e->shard_timing) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); e->shard_events.push_back(ev); } };
+    mark();
     k_sweep<<<dim3(e->sweep_blocks, 1), SW_THREADS, 0, st>>>(G);
+    mark();
     k_expose<<<dim3(e->list_blocks, 1), EX_THREADS, 0, st>>>(G);
-    if (G.xp2p) k_publish<<<1, 32, 0, st>>>(G);
+    mark();
+    if (G.xp2p) { k_publish<<<1, 32, 0, st>>>(G); k_wait<<<1, 32, 0, st>>>(G); }      // raise the own flag, wait for every peer's
     else NK(g_nccl.AllGather(G.xbuf + (size_t)G.rank * G.xslot, G.xbuf, G.xslot, ncclChar, e->comm, st));
+    mark();
     k_merge<<<e->merge_blocks, 256, 0, st>>>(G);
-    if (last) { k_resolve<false><<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G); launch_boundary(e, 1, 1, st, G); }
-    else { k_resolve<true><<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G); launch_boundary(e, 2, 1, st, G); }
-    e->launches += 5;
+    mark();
+    if (last) k_resolve<false><<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G); else k_resolve<true><<<dim3(e->resolve_blocks, 1), 256, 0, st>>>(G);
+    mark();
+    launch_boundary(e, last ? 1 : 2, 1, st, G);
+    mark();
+    e->launches += G.xp2p ? 7 : 5;
     return 0;
 }
 
@@ -653,6 +666,15 @@ extern "C" int rb_sync(rb_engine *e) {
     CK(cudaStreamSynchronize(e->stream));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_ms = ms; else cudaGetLastError();
+    if (!e->shard_events.empty()) {
+        double t[6] = {0, 0, 0, 0, 0, 0};
+        for (size_t d = 0; d + 7 <= e->shard_events.size(); d += 7)
+            for (int k = 0; k < 6; k++) { float x = 0; if (cudaEventElapsedTime(&x, e->shard_events[d + k], e->shard_events[d + k + 1]) == cudaSuccess) t[k] += x; }
+        fprintf(stderr, "[rank %d] %zu days: sweep %.2f  expose %.2f  exchange+wait %.2f  merge %.2f  resolve %.2f  boundary %.2f ms (step %.2f)\n",
+                e->G.rank, e->shard_events.size() / 7, t[0], t[1], t[2], t[3], t[4], t[5], e->last_ms);
+        for (cudaEvent_t ev : e->shard_events) cudaEventDestroy(ev);
+        e->shard_events.clear();
+    }
     return 0;
 }
 
