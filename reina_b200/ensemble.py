@@ -45,6 +45,29 @@ def mean_std(s1, s2, n):
     return mean, np.sqrt(var)
 
 
+def percentile_bands(rows, q=(5, 25, 50, 75, 95)):
+    """Uncertainty bands of an ensemble: rows[replica, day, series] -> {q: [day, series]} (what the reference's UI would
+    draw from run_monte_carlo's reina_<scenario>.csv, calc/simulation.py:365-385)."""
+    x = np.asarray(rows, dtype=np.float64)
+    p = np.percentile(x, list(q), axis=0)
+    return {int(k): p[i] for i, k in enumerate(q)}
+
+
+def gather_rows(rows):
+    """All ranks' stats rows on every rank (percentiles need the members, not just the moments): all_gather over the
+    process group, identity without one."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return np.asarray(rows)
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(rows))
+    if dist.get_backend() == 'nccl':
+        t = t.cuda()
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return np.concatenate([o.cpu().numpy() for o in out], axis=0)
+
+
 def seeds_for_rank(seed0, replicas_per_rank, rank):
     """Replica r of rank k uses seed seed0 + k * R + r (Context adds r itself)."""
     return seed0 + rank * replicas_per_rank

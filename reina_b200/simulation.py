@@ -127,13 +127,16 @@ def sample_model_parameters(what, age, severity=None, variables=None):
 
 
 def run_monte_carlo(scenario_name='default', n_seeds=1000, seed0=0, variables=None, replicas_per_launch=64,
-                    device=0, csv_path=None):
+                    device=0, csv_path=None, bands=None, context=None):
     """Working replacement of calc/simulation.py:365-385: `n_seeds` runs of one scenario, `replicas_per_launch`
     at a time on the GPU; returns the long DataFrame (date, columns..., run, scenario) and writes
-    reina_<scenario>.csv like the reference does."""
+    reina_<scenario>.csv like the reference does.  With `bands=(5, 50, 95)` also returns the percentile bands of every
+    column per day: {q: DataFrame[date x columns]}."""
     import pandas as pd
     v = variables or inputs.default_variables()
-    ctx = make_context(v, n_replicas=replicas_per_launch, device=device, scenario=scenario_name)
+    scenario = None if scenario_name in (None, 'default') else scenario_name
+    ctx = context or make_context(v, n_replicas=replicas_per_launch, device=device, scenario=scenario)
+    replicas_per_launch = ctx.n_replicas
     days = v['simulation_days']
     dfs = []
     for first in range(seed0, seed0 + n_seeds, replicas_per_launch):
@@ -144,13 +147,19 @@ def run_monte_carlo(scenario_name='default', n_seeds=1000, seed0=0, variables=No
             df, _ = rows_to_frames(ctx, rows[r], v['start_date'])
             df['run'] = first + r
             dfs.append(df)
+    out = None
+    if bands:
+        from . import ensemble
+        cols = [c for c in dfs[0].columns if c not in ('run', 'us_per_infected')]
+        cube = np.stack([d[cols].to_numpy(dtype=np.float64) for d in dfs])          # [run, day, column]
+        out = {q: pd.DataFrame(p, index=dfs[0].index, columns=cols) for q, p in ensemble.percentile_bands(cube, bands).items()}
     df = pd.concat(dfs)
     df.index.name = 'date'
     df = df.reset_index()
     df['scenario'] = scenario_name
     if csv_path is not False:
         df.to_csv(csv_path or 'reina_%s.csv' % scenario_name, index=False)
-    return df
+    return (df, out) if bands else df
 
 
 def main(argv=None):

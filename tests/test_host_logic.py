@@ -177,3 +177,61 @@ def test_simulate_individuals_shapes(oracle_lib):
         simulation.simulate_individuals(v, context=helpers.make_context(
             oracle_lib, variables=v, age_count_override=helpers.small_population(4000), max_days=30),
             step_callback=lambda d: False)
+
+
+def test_monte_carlo_driver_and_percentile_bands(oracle_lib, tmp_path):
+    """run_monte_carlo (calc/simulation.py:365-385 made to work): long frame with run / scenario columns, the csv the
+    reference writes, and percentile bands per day."""
+    from reina_b200 import ensemble, simulation
+    v = inputs.default_variables(simulation_days=30)
+    ctx = helpers.make_context(oracle_lib, variables=v, age_count_override=helpers.small_population(6000), n_replicas=4, max_days=31)
+    csv = tmp_path / 'reina_default.csv'
+    df, bands = simulation.run_monte_carlo('default', n_seeds=10, seed0=100, variables=v, context=ctx, csv_path=str(csv),
+                                           bands=(5, 50, 95))
+    assert sorted(df['run'].unique()) == list(range(100, 110))           # the last launch is only partly used
+    assert len(df) == 10 * 30 and set(df['scenario']) == {'default'} and csv.exists()
+    assert set(bands) == {5, 50, 95} and bands[50].shape == (30, 25)
+    assert (bands[5].to_numpy() <= bands[50].to_numpy()).all() and (bands[50].to_numpy() <= bands[95].to_numpy()).all()
+    per_run = df.pivot(index='date', columns='run', values='all_infected').to_numpy()
+    assert np.allclose(bands[50]['all_infected'].to_numpy(), np.percentile(per_run, 50, axis=1))
+    # replica r of a launch == the single run with that seed
+    single = helpers.make_context(oracle_lib, variables=v, age_count_override=helpers.small_population(6000), seed=105, max_days=31)
+    one, _ = simulation.simulate_individuals(v, context=single)
+    assert np.array_equal(one['all_infected'].to_numpy(), df[df['run'] == 105]['all_infected'].to_numpy())
+    cube = np.arange(24, dtype=float).reshape(4, 3, 2)
+    assert np.allclose(ensemble.percentile_bands(cube, (0, 100))[100], cube[3]) and np.allclose(ensemble.gather_rows(cube), cube)
+
+
+def test_serving_worker_reuses_contexts(oracle_lib):
+    """The long-lived worker of reina_b200.serving (replaces a process per request, simulation_thread.py:14-61):
+    results / finished / error entries, context reuse across seeds, a new context for other inputs, cancellation."""
+    from reina_b200 import serving, simulation
+    built = []
+
+    def factory(v, scenario):
+        built.append(v['simulation_days'])
+        return helpers.make_context(oracle_lib, variables=v, scenario=scenario, seed=v['random_seed'],
+                                    age_count_override=helpers.small_population(5000), max_days=v['simulation_days'] + 1)
+
+    w = serving.SimulationWorker(context_factory=factory, callback_day_interval=10, max_contexts=2)
+    v = inputs.default_variables(simulation_days=25)
+    jobs = []
+    for seed in (7, 8):
+        vv = dict(v); vv['random_seed'] = seed
+        jobs.append(w.submit(vv))
+    res = [w.wait(j, timeout=120) for j in jobs]
+    assert all(r['finished'] and r['error'] is None for r in res)
+    assert [r['reused_context'] for r in res] == [False, True] and built == [25]
+    assert res[0]['total'].shape == (25, 26) and res[0]['age_groups'].shape == (25, 12 * 9)
+    assert not res[0]['total']['all_infected'].equals(res[1]['total']['all_infected'])      # different seeds
+    vv = dict(v); vv['random_seed'] = 8
+    direct, _ = simulation.simulate_individuals(vv, context=factory(vv, None))
+    assert np.array_equal(direct['all_infected'].to_numpy(), res[1]['total']['all_infected'].to_numpy())
+    v2 = inputs.default_variables(simulation_days=12)
+    r2 = w.wait(w.submit(v2), timeout=120)
+    assert r2['finished'] and not r2['reused_context'] and r2['total'].shape[0] == 12
+    # a failing request reports its error like the reference's <key>-error entry
+    bad = dict(v); bad['interventions'] = [['no-such-intervention', '2020-02-20']]
+    r3 = w.wait(w.submit(bad), timeout=120)
+    assert r3['finished'] and r3['error']
+    w.close()
