@@ -3,18 +3,20 @@
 //
 //   state.cuh     data layout in HBM (agents stored AGE-SORTED, so age is implied by position and a contact target is
 //                 age_start[band] + u32 % band_size with no indirection), per-replica counters, shared device helpers
-//   boundary.cuh  k_pre / k_post / k_between, 1 CTA per replica: stats row, intervention deltas, imports, test queue +
-//                 contact tracing, vaccination, sweep start; beds / ICU first-come-first-served = sort by sweep
-//                 position + max-plus scan
+//   boundary.cuh  k_pre / k_post / k_between, one CTA per replica or (few replicas of a large population) a team of
+//                 co-resident CTAs with a grid barrier: stats row, intervention deltas, imports, test queue + contact
+//                 tracing, vaccination, sweep start; beds / ICU first-come-first-served = sort by sweep position +
+//                 max-plus scan
 //   sweep.cuh     k_sweep: Context._iterate_people / person_advance over the active agents; emits contact work items,
 //                 capacity events and test-queue entries tagged with sweep position
 //   contacts.cuh  k_expose: one thread per group of four sampled contacts (row search, target gather, transmission draw,
 //                 atomicMin(winner[target], sweep position of infector | slot)); k_resolve: winners become infected
-//   shard.cuh     k_merge: population-sharded mode, applies every rank's message after the daily all-gather
+//   shard.cuh     population-sharded mode: k_publish / k_wait (per-day flags in NVLink peer memory) and k_merge, which
+//                 pulls and applies every rank's message of the day
 //   setup.cuh     set_initial_state, initialisation, snapshot, ensemble moments, samplers
 //   this file     host side: engine handle, launch geometry, CUDA graphs, NCCL binding, the extern "C" entry points
 //
-// Per day (reference order, main.pyx:1994-2016): k_sweep -> k_expose -> k_resolve -> k_between.  Every order-dependent
+// Per day and replica group (reference order, main.pyx:1994-2016): k_sweep -> k_expose -> k_resolve -> k_between.  Every order-dependent
 // step of the sequential reference is resolved through the agent's sweep position, so the result is bit-identical to the
 // sequential CPU oracle and independent of scheduling.
 #include "state.cuh"
@@ -59,6 +61,7 @@ struct rb_engine {
     // replica groups: the ensemble is split into n_groups sets of replicas, each advanced by its own chain of launches
     // on its own stream with a grid sized for its share of the SMs.  The groups run half a day apart, so the
     // latency-bound phases of one (k_resolve, the single-CTA day boundary) overlap the sweep / contact kernels of another.
+    cudaError_t launch_err;             // first failed cooperative launch (launch_boundary)
     int wide_ctas;                      // CTAs per replica of the wide day boundary (<= 1: one CTA per replica)
     int n_groups;
     ReplicaGroup grp[MAX_GROUPS];
@@ -170,7 +173,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     if (const char *s = getenv("RB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(s));   // measurement aid
     rb_engine *e = new rb_engine();
     e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0; e->have_graphs = false; e->comm = nullptr; e->merge_blocks = 1;
-    e->has_ipc = false; e->n_groups = 1; e->wide_ctas = 1; e->n_peer_open = 0; e->shard_timing = getenv("RB_SHARD_TIMING") != nullptr;
+    e->has_ipc = false; e->n_groups = 1; e->wide_ctas = 1; e->n_peer_open = 0; e->launch_err = cudaSuccess; e->shard_timing = getenv("RB_SHARD_TIMING") != nullptr;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     Eng &G = e->G;
@@ -396,9 +399,11 @@ static void launch_boundary(rb_engine *e, int kind, int R, cudaStream_t st, cons
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;     // all CTAs co-resident: the team's grid barrier needs it
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (kind == 0) cudaLaunchKernelEx(&cfg, k_pre<true>, G);
-    else if (kind == 1) cudaLaunchKernelEx(&cfg, k_post<true>, G);
-    else cudaLaunchKernelEx(&cfg, k_between<true>, G);
+    cudaError_t err;
+    if (kind == 0) err = cudaLaunchKernelEx(&cfg, k_pre<true>, G);
+    else if (kind == 1) err = cudaLaunchKernelEx(&cfg, k_post<true>, G);
+    else err = cudaLaunchKernelEx(&cfg, k_between<true>, G);
+    if (err != cudaSuccess && e->launch_err == cudaSuccess) e->launch_err = err;     // reported by the rb_step that issued it
 }
 
 // One "segment" = the grid kernels of day d followed by the fused day boundary d -> d+1.
@@ -588,6 +593,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
         for (int d = 0; d < n_days; d++) if (launch_day_sharded(e, d == n_days - 1)) return 1;
         CK(cudaEventRecord(e->ev1, e->stream));
         CK(cudaGetLastError());
+        if (e->launch_err != cudaSuccess) { snprintf(g_err, sizeof g_err, "cooperative launch of the day boundary failed: %s", cudaGetErrorString(e->launch_err)); return 1; }
         e->day += n_days;
         return 0;
     }
@@ -614,6 +620,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
         }
         CK(cudaEventRecord(e->ev1, e->stream));
         CK(cudaGetLastError());
+        if (e->launch_err != cudaSuccess) { snprintf(g_err, sizeof g_err, "cooperative launch of the day boundary failed: %s", cudaGetErrorString(e->launch_err)); return 1; }
         e->day += n_days;
         return 0;
     }
@@ -629,6 +636,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     e->launches += 4;
     CK(cudaEventRecord(e->ev1, e->stream));
     CK(cudaGetLastError());
+    if (e->launch_err != cudaSuccess) { snprintf(g_err, sizeof g_err, "cooperative launch of the day boundary failed: %s", cudaGetErrorString(e->launch_err)); return 1; }
     e->day += n_days;
     return 0;
 }
