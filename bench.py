@@ -122,7 +122,8 @@ def algorithmic_bytes(s1, n_agents, n_replicas, G):
     sweep = 4.0 * n_agents * n_replicas * D + 12.0 * I.sum()
     total = sweep + 8.0 * E.sum()
     return dict(sweep=sweep, total=total, mean_infected=float(I.mean() / n_replicas),
-                mean_contacts=float(E[1:].mean() / n_replicas) if D > 1 else 0.0)
+                mean_contacts=float(E[1:].mean() / n_replicas) if D > 1 else 0.0,
+                daily_infected=(I / n_replicas).tolist(), daily_contacts=(E / n_replicas).tolist())
 
 
 def cpu_baseline(days, seeds, processes):
@@ -182,6 +183,7 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-single', action='store_true')
+    ap.add_argument('--dump-daily', default=None, help='write the per-day I_d, E_d (ensemble means) the algorithmic bytes are computed from')
     a = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -257,6 +259,12 @@ def main():
     value = agent_days_step / (ms_per_step / 1e3)
     e2e_value = agent_days_step / (wall_total / a.steps)
     alg = algorithmic_bytes(s1, N_AGENTS, R, G)
+
+    if a.dump_daily and rank == 0:
+        with open(a.dump_daily, 'w') as f:
+            json.dump(dict(note='HUS, ensemble means over %d seeds of the last timed step: I_d = infected at the start of day d, '
+                                'E_d = contacts sampled on day d-1 (stats row d); bytes_d = 4 N + 12 I_d + 8 E_d (SURVEY.md 8d)' % R,
+                           agents=N_AGENTS, days=D, I_d=alg['daily_infected'], E_d=alg['daily_contacts']), f)
 
     # ---------------- per-kernel device times (one extra run, events around every launch) ----------------
     ctx.reset(seed_of(a.warmup + a.steps - 1))
