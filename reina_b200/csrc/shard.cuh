@@ -25,7 +25,7 @@ __global__ void k_wait(Eng G) {
         const long long t0 = clock64();
         while ((int32_t)(*flag - want) < 0) {
             __nanosleep(200);
-            if (clock64() - t0 > 20000000000ll) { set_problem(c, RB_OTHER_FAILURE); break; }     // ~10 s: a peer died; fail loudly, do not hang
+            if (clock64() - t0 > 120000000000ll) { set_problem(c, RB_OTHER_FAILURE); break; }    // ~1 min: a peer died; fail loudly, do not hang
         }
         __threadfence_system();
     }

@@ -31,7 +31,13 @@ def _worker(rank, world, port, out_dir):
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     res = ensemble.run_ensemble(_make, days=50, replicas_per_rank=2, seed0=300, rank=rank)
-    np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), mean=res['mean'], std=res['std'], n=res['n'])
+    # percentile bands need the members, not just the moments: all ranks' rows are gathered over the process group
+    ctx = _make(2, ensemble.seeds_for_rank(300, 2, rank))
+    ctx.run(50)
+    rows = ensemble.gather_rows(ctx.series(0, 50))
+    bands = ensemble.percentile_bands(rows, (0, 50, 100))
+    np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), mean=res['mean'], std=res['std'], n=res['n'],
+             n_rows=rows.shape[0], lo=bands[0], median=bands[50], hi=bands[100])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,3 +52,9 @@ def test_two_rank_ensemble_equals_single_process(tmp_path):
     mean, std = ensemble.mean_std(*ensemble.curve_moments(ctx.series(0, 50)))
     np.testing.assert_allclose(r0['mean'], mean, rtol=1e-12, atol=1e-9)
     np.testing.assert_allclose(r0['std'], std, rtol=1e-9, atol=1e-6)
+    # bands over the gathered members == bands of the one-process ensemble, identical on both ranks
+    one = ensemble.percentile_bands(ctx.series(0, 50), (0, 50, 100))
+    assert int(r0['n_rows']) == 4
+    for name, q in (('lo', 0), ('median', 50), ('hi', 100)):
+        assert np.array_equal(r0[name], r1[name])
+        np.testing.assert_allclose(r0[name], one[q])
