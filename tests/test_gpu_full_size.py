@@ -19,6 +19,7 @@ GOLD = os.path.join(helpers.ROOT, 'tests', 'golden')
     ('hus_hammer_and_dance', 'HUS', 'hammer-and-dance'),           # configs[2]: contact tracing 30 -> 60 %
     ('hus_mitigation', 'HUS', 'mitigation'),                       # configs[2]: capacity building + mobility
     ('hus_summer_boogie', 'HUS', 'summer-boogie'),
+    ('hus_looser_restrictions', 'HUS', 'looser-restrictions-to-start-with'),   # configs[2]: every limit-mobility value halved
     ('hus_initial_state', 'HUS', None),                            # Population.set_initial_state, start 2020-04-01
 ])
 def test_ensemble_statistics_match_reference(cuda_lib, gold_name, area, scenario):
