@@ -99,6 +99,32 @@ def test_contact_tables_match_pandas_restatement():
     np.testing.assert_allclose(emp, cdf[30, 0, :6], atol=4e-3)
 
 
+@pytest.mark.parametrize('seed', range(8))
+def test_contact_tables_random_mobility_sequences(seed):
+    """Random sequences of limit-mobility settings (keys stack multiplicatively, a repeated key is overwritten,
+    main.pyx:1250-1266) against the pandas restatement of generate_contact_probabilities."""
+    rng = np.random.default_rng(100 + seed)
+    cm = model.ContactMatrix(inputs.contacts_long(), 101)
+    for _ in range(int(rng.integers(1, 9))):
+        place = None if rng.random() < 0.3 else int(rng.integers(0, 6))
+        lo = None if rng.random() < 0.4 else int(rng.integers(0, 80))
+        hi = None if rng.random() < 0.4 else int(rng.integers(lo or 0, 101))
+        cm.set_mobility_factor(float(rng.choice([0.0, 0.05, 0.2, 0.5, 0.8, 1.0])), place=place, min_age=lo, max_age=hi)
+    if all(f[3] == 0.0 for f in cm.mobility_factors if f[0] == model.PLACE_ALL and f[1] == 0 and f[2] == 100) and \
+            any(f[0] == model.PLACE_ALL and f[1] == 0 and f[2] == 100 for f in cm.mobility_factors):
+        pytest.skip('all contacts switched off for everybody: the reference divides by zero there too')
+    t = cm.generate()
+    total, cum, index = _pandas_tables(cm)
+    nk = len(cm.keys)
+    ok = total > 0                      # an age whose every contact is switched off has no distribution (0 / 0) on both sides
+    np.testing.assert_allclose(t['nr_contacts'], total, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(t['cum_p'][ok, :nk], cum[ok], rtol=0, atol=1e-12)
+    assert (np.diff(t['cum_p'][ok, :nk], axis=1) >= -1e-15).all()
+    assert np.all(np.abs(t['cum_p'][ok, nk - 1] - 1.0) < 1e-12)
+    cdf = t['ncontact_cdf']
+    assert (np.diff(cdf, axis=2) >= 0).all() and (cdf <= 1).all() and (cdf >= 0).all()
+
+
 def test_intervention_tuples_and_schedule(oracle_lib):
     ivs = inputs.active_interventions()
     assert len(ivs) == 40 and ivs[6].get_param_values() == dict(reduction=80, min_age=0, max_age=70, place='other')
