@@ -33,6 +33,10 @@ CONFIGS = {
     # Population.set_initial_state (main.pyx:1452-1516): a start date the HUS case file holds (9 dead, 32 in ICU, 52 in
     # ward, 1200 confirmed) + the example values of variables.py:212-214 for the unmeasurable part
     'hus_initial_state': ('HUS', None, 180),
+    # every intervention type (imports of both variants, weekly trickle, all testing modes, contact tracing at three
+    # efficiencies, masks, age / place mobility limits, three vaccination updates, capacity building) on an 80,000-agent
+    # HUS-shaped population with a tiny hospital that saturates: tests/helpers.py stress_interventions(), 256 seeds
+    'hus80k_every_intervention': ('HUS', None, 120),
 }
 VARIABLE_OVERRIDES = {
     'hus_initial_state': dict(start_date='2020-04-01', incubating_at_simulation_start=150, ill_at_simulation_start=50,
@@ -56,8 +60,17 @@ def main():
             from reina_b200 import inputs
             variables = inputs.default_variables()
             variables.update(VARIABLE_OVERRIDES[name])
+        extra = {}
+        if name == 'hus80k_every_intervention':
+            sys.path.insert(0, os.path.join(ROOT, 'tests'))
+            import helpers
+            from reina_b200 import inputs
+            seeds = np.arange(a.seed0, a.seed0 + max(a.seeds, 256))
+            variables = inputs.default_variables()
+            variables['hospital_beds'], variables['icu_units'] = 25, 3
+            extra = dict(age_count_override=helpers.small_population(80000), interventions=helpers.stress_interventions())
         series, t_iter, wall = ref_harness.run_ensemble(seeds, days=days, processes=a.processes,
-                                                        area=area, scenario=scenario, variables=variables)
+                                                        area=area, scenario=scenario, variables=variables, **extra)
         out = os.path.join(HERE, 'ref_ensemble_%s.npz' % name)
         np.savez_compressed(
             out, mean=series.mean(axis=0), std=series.std(axis=0, ddof=1), n=len(seeds),

@@ -56,6 +56,39 @@ def test_ensemble_means_within_3_standard_errors():
         assert abs(z[-1, names.index(s)]) < 3.0, (s, z[-1, names.index(s)])
 
 
+def _oracle_run_every_intervention(seed):
+    v = helpers.inputs.default_variables()
+    v['hospital_beds'], v['icu_units'] = 25, 3
+    ctx = helpers.make_context(helpers.oracle_library(), area='HUS', variables=v, seed=seed, max_days=121,
+                               age_count_override=helpers.small_population(80000), interventions=helpers.stress_interventions())
+    ctx.run(120)
+    return helpers.series_matrix(ctx)[0]
+
+
+def test_every_intervention_type_matches_reference():
+    """The schedule of tests/helpers.py stress_interventions() -- imports of both variants, weekly trickle with a variant
+    share, every testing mode, contact tracing at 60 / 100 / 35 %, masks, age / place mobility limits, three vaccination
+    updates, capacity building, a 25-bed / 3-ICU hospital that saturates -- on 80,000 agents: 256 oracle seeds against
+    256 seeds of the unmodified reference (tests/golden/make_golden.py 'hus80k_every_intervention').  The CUDA engine is
+    bit-exact against the oracle on this very schedule (tests/test_gpu_parity.py::test_every_intervention_type)."""
+    gold = np.load(os.path.join(GOLD, 'ref_ensemble_hus80k_every_intervention.npz'))
+    with ProcessPoolExecutor(min(8, os.cpu_count() or 1)) as ex:
+        runs = list(ex.map(_oracle_run_every_intervention, [9000 + s for s in range(256)]))
+    mine = np.stack(runs)
+    names = list(gold['names'])
+    assert names == helpers.series_names()
+    z, exact = zscores(mine, gold)
+    assert not exact.any(), 'deterministic series differ: %s' % sorted({names[j] for j in np.argwhere(exact)[:, 1]})
+    frac = (np.abs(z) > 3).mean()
+    worst = np.unravel_index(np.abs(z).argmax(), z.shape)
+    assert frac < 0.015, 'fraction of cells beyond 3 SE: %.4f' % frac
+    assert np.abs(z).max() < 5.0, 'worst cell: day %d %s z=%.2f' % (worst[0], names[worst[1]], z[worst])
+    for s in ('all_infected', 'dead', 'all_detected', 'recovered', 'cum_icu', 'vaccinated', 'in_ward'):
+        assert abs(z[-1, names.index(s)]) < 3.0, (s, z[-1, names.index(s)])
+    assert gold['mean'][-1, names.index('vaccinated')] > 25000 and gold['mean'][:, names.index('ct_cases_per_day')].max() > 50
+    assert gold['mean'][:, names.index('available_hospital_beds')].min() < 1.0          # the ward saturates in the reference too
+
+
 INITIAL_STATE_VARIABLES = dict(start_date='2020-04-01', incubating_at_simulation_start=150, ill_at_simulation_start=50,
                                recovered_at_simulation_start=1000)      # tests/golden/make_golden.py, 'hus_initial_state'
 
