@@ -261,3 +261,47 @@ def test_serving_worker_reuses_contexts(oracle_lib):
     r3 = w.wait(w.submit(bad), timeout=120)
     assert r3['finished'] and r3['error']
     w.close()
+
+
+def test_surface_equals_the_reference_module(oracle_lib):
+    """Side by side with the UNMODIFIED reference module (oracle/_ref): module constants, the keys / dtypes / shapes of
+    generate_state(), get_population_stats(), get_date_for_today() and the exception behaviour."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip('oracle/_ref not built')
+    ref_model = ref_harness.load_model()
+    assert tuple(ref_model.DISEASE_PARAMS) == tuple(model.DISEASE_PARAMS)
+    assert dict(ref_model.SEVERITY_TO_STR) == model.SEVERITY_TO_STR and dict(ref_model.STATE_TO_STR) == model.STATE_TO_STR
+    assert dict(ref_model.PROBLEM_TO_STR) == model.PROBLEM_TO_STR
+    assert issubclass(ref_model.SimulationFailed, Exception) and issubclass(model.SimulationFailed, Exception)
+    counts = helpers.small_population(8000)
+    ref = ref_harness.make_context(age_count_override=counts, seed=3)
+    mine = helpers.make_context(oracle_lib, age_count_override=counts, seed=3)
+    for day in range(3):
+        a, b = ref.generate_state(), mine.generate_state()
+        assert set(a) == set(b), set(a) ^ set(b)
+        for k in a:
+            if isinstance(a[k], np.ndarray):
+                assert a[k].dtype == b[k].dtype == np.int32 and a[k].shape == b[k].shape, k
+            elif isinstance(a[k], dict):
+                assert list(a[k]) == list(b[k]), k
+            else:
+                assert isinstance(b[k], (int, float)), k
+        if day == 0:        # before the first iterate() nothing is random: the rows are equal
+            for k in a:
+                if isinstance(a[k], np.ndarray):
+                    assert np.array_equal(a[k], b[k]), k
+                elif isinstance(a[k], dict):
+                    assert a[k] == b[k], k
+                else:
+                    assert abs(a[k] - b[k]) < 1e-6, k
+        assert ref.get_date_for_today() == mine.get_date_for_today()
+        ref.iterate(); mine.iterate()
+    for what in ('dead', 'all_infected', 'all_detected'):
+        ra, rb = np.asarray(ref.get_population_stats(what)), np.asarray(mine.get_population_stats(what))
+        assert ra.shape == rb.shape and ra.dtype.kind == rb.dtype.kind == 'i', what
+    for ctx in (ref, mine):
+        with pytest.raises(Exception):
+            ctx.get_population_stats('nonsense')
+        with pytest.raises(Exception):
+            ctx.apply_intervention(inputs.Intervention('no-such-intervention', '2020-01-01'))
