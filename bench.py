@@ -1,14 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- agent-days/sec of the per-day agent loop on the HUS configuration (BASELINE.json).
+"""bench.py -- agent-days/sec of the per-day agent loop (BASELINE.json), measured on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--replicas R] [--days D] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload hus|varsinais|scenario:<name>|synth50m]
+                    [--replicas R | --total-seeds T] [--days D] [--impl reference]
 
-A "step" is one complete HUS run (1,685,983 agents x 180 days, the reference's default interventions) of an
-ensemble of R seeds per GPU, every step with fresh seeds.  `value` times only the device-resident multi-day run
-(CUDA events on the engine's stream, inputs already in HBM); `e2e` times the same step through the public API
-(`Context.reset` + `upload_inputs` + `run` + `series`) with host buffers, host->device and device->host copies
-included.  For N > 1 (torchrun, one rank per GPU) the ensemble is partitioned over the GPUs -- independent units,
-weak scaling -- and the only collective is the final NCCL all-reduce of the daily curves (sum and sum of squares).
+Default workload `hus`: a "step" is one complete HUS run (1,685,983 agents x 180 days, the reference's default
+interventions; BASELINE configs[1]) of an ensemble of R seeds per GPU advanced by the same launches (configs[3]), every
+step with fresh seeds.  `value` times only the device-resident multi-day run (CUDA events on the engine's stream, inputs
+already in HBM); `e2e` times the same step through the public API (`Context.reset` + `upload_inputs` + `run` +
+`moments`) with host buffers, host->device and device->host copies included.  For N > 1 (one rank per GPU, launched by
+torchrun) the ensemble is partitioned over the GPUs -- independent units, no data-path collective -- and the only
+exchange is the final ncclAllReduce of the daily curves, issued by the engine itself (rb_reduce_moments); barrier and
+max-over-ranks go through the same communicator.  No torch anywhere in this file.
+
+    --replicas R       R seeds PER GPU (weak scaling, the default: 256)
+    --total-seeds T    T seeds in total, T / N per GPU (configs[3] as written: strong scaling)
+    --workload varsinais | scenario:hammer-and-dance | scenario:mitigation | ...   the other ensemble configurations
+    --workload synth50m  configs[4]: ONE synthetic 5e7-agent population, population-sharded over the N GPUs
+
+The default run also reports, beside the headline: the 256-total-seed strong-scaling point (N > 1), the synthetic
+50 M-agent population on the same N GPUs, the single-seed run, per-kernel device times in the production launch
+geometry and in isolation, and the reference's Cython engine on this box's host cores (N = 1).
 
 `--impl reference` times the UNMODIFIED reference engine (oracle/_ref, built from /root/reference by
 oracle/build_ref.sh) on this box's host cores: one seed per core, same workload and metric.
@@ -26,27 +38,97 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-AREA = 'HUS'
-N_AGENTS = 1685983
+N_HUS = 1685983
+N_SYNTH = 50_000_000
 
 
-def load_sweep_traffic(n_replicas):
-    """Mean DRAM bytes (read + write) per k_sweep launch over the 180 launches of one run, from the committed ncu pass
-    (profiles/: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` on every k_sweep launch,
-    tools/collect_profiles.sh).  Only valid for the replica count it was captured at."""
-    p = os.path.join(ROOT, 'profiles', 'r01_launches_and_sweep_traffic_R%d.json' % n_replicas)
-    if not os.path.exists(p):
-        return None
-    with open(p) as f:
-        return float(json.load(f)['k_sweep_dram']['mean_traffic_bytes'])
+# ---------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------
+def workload_spec(name):
+    """-> dict(area, scenario, label, config) for the ensemble workloads."""
+    if name == 'hus':
+        return dict(area='HUS', scenario=None, label='HUS 1,685,983 agents, default interventions (BASELINE configs[1] / [3])')
+    if name == 'varsinais':
+        return dict(area='Varsinais-Suomi', scenario=None, label='Varsinais-Suomi 479,861 agents, default interventions (BASELINE configs[0])')
+    if name.startswith('scenario:'):
+        sc = name.split(':', 1)[1]
+        return dict(area='HUS', scenario=sc, label='HUS 1,685,983 agents, scenario %s (BASELINE configs[2])' % sc)
+    raise SystemExit('unknown workload %r' % name)
 
 
+def metric_name(workload):
+    return 'agent-days/sec (HUS 1.7M)' if workload == 'hus' else 'agent-days/sec (%s)' % workload
+
+
+def make_context(spec, n_replicas, device, days, seed):
+    from reina_b200 import inputs, model
+    v = inputs.default_variables()
+    args = inputs.build_context_args(v, area=spec['area'])
+    args['random_seed'] = seed
+    ctx = model.Context(n_replicas=n_replicas, device=device, max_days=days + 1, **args)
+    for iv in inputs.active_interventions(v, spec['scenario']):
+        ctx.add_intervention(iv)
+    return ctx
+
+
+def make_synth_context(n_agents, device, days, shard):
+    """BASELINE configs[4]: HUS age histogram scaled to n_agents, capacity and imports scaled alike."""
+    from reina_b200 import inputs, model
+    f = n_agents / float(N_HUS)
+    v = inputs.default_variables()
+    v['hospital_beds'], v['icu_units'] = int(round(2600 * f)), int(round(300 * f))
+    ivs = []
+    for iv in v['interventions']:
+        iv = list(iv)
+        if iv[0] in ('import-infections', 'import-infections-weekly'):
+            iv[2] = int(round(iv[2] * f))
+        ivs.append(iv)
+    v['interventions'] = ivs
+    args = inputs.build_context_args(v, age_count_override=inputs.synthetic_age_counts(n_agents))
+    args['random_seed'] = 0
+    ctx = model.Context(n_replicas=1, device=device, max_days=days + 1, shard=shard, **args)
+    for iv in inputs.active_interventions(v):
+        ctx.add_intervention(iv)
+    return ctx
+
+
+# ---------------------------------------------------------------------------------------------------
+# measurement helpers
+# ---------------------------------------------------------------------------------------------------
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         with open(p) as f:
             return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def kernel_source_stamp():
+    """sha1 over the CUDA sources: an ncu traffic capture is only valid for the kernels it was taken from."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, 'reina_b200', 'csrc')
+    for name in sorted(os.listdir(d)):
+        with open(os.path.join(d, name), 'rb') as f:
+            h.update(name.encode() + b'\0' + f.read())
+    return h.hexdigest()
+
+
+def load_traffic(kernel, n_replicas, days):
+    """Mean DRAM bytes (read + write) per launch of `kernel` from the committed ncu pass (profiles/r02_dram_traffic_R<R>.json,
+    written by tools/ncu_traffic.py with the source stamp of the kernels it measured).  None -- never a stale number -- if
+    the sources have changed since, or the capture was taken at another replica count / run length."""
+    p = os.path.join(ROOT, 'profiles', 'r02_dram_traffic_R%d.json' % n_replicas)
+    if not os.path.exists(p):
+        return None, 'no capture for R=%d' % n_replicas
+    with open(p) as f:
+        t = json.load(f)
+    if t.get('source_stamp') != kernel_source_stamp():
+        return None, 'capture is stale (kernel sources changed since)'
+    if t.get('days') != days or kernel not in t.get('kernels', {}):
+        return None, 'capture does not cover this run'
+    return float(t['kernels'][kernel]['mean_traffic_bytes']), t.get('command')
 
 
 class ClockSampler:
@@ -99,17 +181,6 @@ class ClockSampler:
                     samples=len(sm), reasons=sorted(reasons))
 
 
-def make_context(n_replicas, device, days, seed):
-    from reina_b200 import inputs, model
-    v = inputs.default_variables()
-    args = inputs.build_context_args(v, area=AREA)
-    args['random_seed'] = seed
-    ctx = model.Context(n_replicas=n_replicas, device=device, max_days=days + 1, **args)
-    for iv in inputs.active_interventions(v):
-        ctx.add_intervention(iv)
-    return ctx
-
-
 def algorithmic_bytes(s1, n_agents, n_replicas, G):
     """bytes_day = 4 N + 12 I_d + 8 E_d, summed over days and replicas.
     s1: [D, row_len] sums over replicas of the stats rows (I_d = infected that day, E_d = contacts sampled that day)."""
@@ -120,57 +191,134 @@ def algorithmic_bytes(s1, n_agents, n_replicas, G):
     E = s1[:, nA * G + _abi.SCALARS.index('exposed_per_day')]            # contacts of day d-1, all replicas
     D = s1.shape[0]
     sweep = 4.0 * n_agents * n_replicas * D + 12.0 * I.sum()
-    total = sweep + 8.0 * E.sum()
-    return dict(sweep=sweep, total=total, mean_infected=float(I.mean() / n_replicas),
+    expose = 8.0 * E.sum()
+    return dict(sweep=sweep, expose=expose, total=sweep + expose, sum_infected=float(I.sum()), sum_contacts=float(E.sum()),
+                mean_infected=float(I.mean() / n_replicas),
                 mean_contacts=float(E[1:].mean() / n_replicas) if D > 1 else 0.0,
                 daily_infected=(I / n_replicas).tolist(), daily_contacts=(E / n_replicas).tolist())
 
 
-def cpu_baseline(days, seeds, processes):
+# ---------------------------------------------------------------------------------------------------
+# CPU arms
+# ---------------------------------------------------------------------------------------------------
+def cpu_baseline(spec, n_agents, days, seeds, processes):
     """The reference's own Cython engine (oracle/_ref) -- or, if it is not built, the C oracle port -- timed on
     this box's host cores: agent-days/s over the summed iterate() time of a bounded sample."""
     from oracle import ref_harness
     if ref_harness.available():
+        ref_harness.load_model()          # in THIS process too: the driver's loaded-library record then shows oracle/_ref
         t0 = time.perf_counter()
-        _, t_iter, wall = ref_harness.run_ensemble(seeds, days=days, processes=processes, area=AREA)
+        _, t_iter, wall = ref_harness.run_ensemble(seeds, days=days, processes=processes, area=spec['area'], scenario=spec['scenario'])
         # rate of each core = agent-days of its run / time spent inside iterate() (setup excluded); cores add up
-        value = float((N_AGENTS * days / t_iter).sum()) if processes > 1 else N_AGENTS * days * len(seeds) / float(t_iter.sum())
+        value = float((n_agents * days / t_iter).sum()) if processes > 1 else n_agents * days * len(seeds) / float(t_iter.sum())
         return dict(value=value, unit='agent-days/s', cores=processes, kind='reference',
-                    sample='%d seed(s) x HUS %d days, unmodified cythonsim engine (oracle/_ref), %s'
-                           % (len(seeds), days, 'sum of iterate() time' if processes == 1 else 'sum over cores of agent-days / iterate() time'),
+                    sample='%d seed(s) x %s %d days, unmodified cythonsim engine (oracle/_ref), %s'
+                           % (len(seeds), spec['area'], days, 'sum of iterate() time' if processes == 1 else 'sum over cores of agent-days / iterate() time'),
                     seconds=time.perf_counter() - t0)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import helpers
     t0 = time.perf_counter()
-    ctx = helpers.make_context(helpers.oracle_library(), area=AREA, seed=int(seeds[0]), max_days=days + 1)
+    ctx = helpers.make_context(helpers.oracle_library(), area=spec['area'], scenario=spec['scenario'], seed=int(seeds[0]), max_days=days + 1)
     ctx.run(days)
     t = time.perf_counter() - t0
-    return dict(value=N_AGENTS * days / t, unit='agent-days/s', cores=1, kind='port',
-                sample='1 seed x HUS %d days, C oracle port (oracle/_ref not built)' % days, seconds=t)
+    return dict(value=n_agents * days / t, unit='agent-days/s', cores=1, kind='port',
+                sample='1 seed x %s %d days, C oracle port (oracle/_ref not built)' % (spec['area'], days), seconds=t)
 
 
 def run_reference(a, rank, world):
     if rank != 0:
         return
+    name = 'hus' if a.workload == 'synth50m' else a.workload      # the reference has no sharded mode: its HUS run stands in
+    spec = workload_spec(name)
+    from reina_b200 import inputs
+    n_agents = int(sum(inputs.build_context_args(inputs.default_variables(), area=spec['area'])['population_params']['age_structure'].values()))
     procs = min(os.cpu_count() or 1, 32)
     vals = []
     for step in range(a.warmup + a.steps):
         if step < a.warmup and step > 0:
             continue        # one warm-up pass is enough to page the extension in; each pass costs ~15 s
         seeds = np.arange(procs) + 100000 + 1000 * step
-        b = cpu_baseline(a.days, seeds, procs)
+        b = cpu_baseline(spec, n_agents, a.days, seeds, procs)
         if step >= a.warmup:
             vals.append(b)
     value = float(np.mean([b['value'] for b in vals]))
-    ms = 1e3 * N_AGENTS * a.days * procs / value
-    out = dict(metric='agent-days/sec (HUS 1.7M)', value=value, unit='agent-days/s', impl='reference',
+    ms = 1e3 * n_agents * a.days * procs / value
+    out = dict(metric=metric_name(name), value=value, unit='agent-days/s', impl='reference',
                n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=ms, higher_is_better=True,
                scaling='weak', vs_baseline=None, dtype='int32/f32 state, f64 uniforms', data='synthetic',
-               config=dict(workload='HUS 1,685,983 agents x %d days, default interventions, %d seeds per step (one per host core)'
-                                    % (a.days, procs)),
+               config=dict(workload='%s x %d days, %d seeds per step (one per host core)' % (spec['label'], a.days, procs)),
                cpu_baseline=dict(value=value, unit='agent-days/s', cores=procs, kind=vals[0]['kind'], sample=vals[0]['sample']),
                e2e=dict(value=value, unit='agent-days/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arms
+# ---------------------------------------------------------------------------------------------------
+def timed_ensemble(ctx, comm, days, steps, warmup, seed_of, sampler=None):
+    """W untimed + K timed steps of the ensemble on `ctx`.  Returns device ms / wall s per step (max over ranks), the last
+    step's replica-summed stats rows, per-step copy volumes and the launch count."""
+    eng = ctx._engine
+
+    def one_step(step):
+        t0 = time.perf_counter()
+        ctx.reset(seed_of(step))                   # fresh ensemble; device state re-initialised in place
+        ctx.upload_inputs()                        # contact tables of every mobility epoch, from host memory
+        ctx.run(days)                              # schedule H2D + the simulated days + sync
+        dev_ms = eng.last_step_ms()                # CUDA events around the multi-day run only
+        s1l, _ = eng.read_moments(0, days)         # this rank's curves (the algorithmic bytes are computed from them)
+        s1, s2, n = ctx.moments(0, days, reduce=True)      # the step's result: k_moments + ONE ncclAllReduce + D2H
+        return dev_ms, time.perf_counter() - t0, s1l
+
+    for step in range(warmup):
+        one_step(step)
+    if sampler:
+        sampler.start()
+    launches0, (h0, d0) = eng.launch_count(), eng.copied_bytes()
+    comm.barrier()
+    dev_ms_total, wall_total, s1 = 0.0, 0.0, None
+    for step in range(warmup, warmup + steps):
+        dev_ms, wall, s1 = one_step(step)
+        dev_ms_total += dev_ms
+        wall_total += wall
+    comm.barrier()
+    clocks = sampler.stop() if sampler else None
+    launches, (h1, d1) = eng.launch_count() - launches0, eng.copied_bytes()
+    dev_ms_total, wall_total = (float(x) for x in comm.allreduce(np.array([dev_ms_total, wall_total]), 'max'))
+    # read_moments above is bookkeeping of this script, not part of the step: take its D2H bytes out again
+    d2h = (d1 - d0) / steps - s1.nbytes * 2
+    return dict(ms_per_step=dev_ms_total / steps, wall_per_step=wall_total / steps, s1=s1, h2d=(h1 - h0) / steps, d2h=d2h,
+                launches=launches, clocks=clocks)
+
+
+def bench_synth(a, rank, world, local, n_agents, days, steps, warmup):
+    """configs[4]: one synthetic population sharded over the ranks.  -> dict for the JSON line (rank 0) / None."""
+    from reina_b200 import comm as rcomm, sharded
+    spec = sharded.shard_spec() if world > 1 else None
+    ctx = make_synth_context(n_agents, local, days, spec)
+    comm = rcomm.EngineComm(ctx._engine) if world > 1 else rcomm.LocalComm()
+    ms, walls = [], []
+    for step in range(warmup + steps):
+        comm.barrier()
+        t0 = time.perf_counter()
+        ctx.reset(1000 + step)                     # the same seed on every rank
+        ctx.run(days)
+        rows = ctx.series(0, days)                 # the run's result on every rank
+        wall = time.perf_counter() - t0
+        t = comm.allreduce(np.array([ctx._engine.last_step_ms(), wall]), 'max')
+        if step >= warmup:
+            ms.append(float(t[0])); walls.append(float(t[1]))
+    G = len(ctx.age_group_labels)
+    chk = float(rows[0, -1, 3 * G:4 * G].sum())
+    lo, hi = float(-comm.allreduce(np.array([-chk]), 'max')[0]), float(comm.allreduce(np.array([chk]), 'max')[0])
+    eng = ctx._engine
+    out = dict(value=n_agents * days / (np.mean(ms) / 1e3), unit='agent-days/s', agents=n_agents, days=days, n_gpus=world,
+               ms_per_run=float(np.mean(ms)), e2e_value=n_agents * days / float(np.mean(walls)), scaling='strong',
+               all_infected_last_day=chk, ranks_agree=bool(lo == hi),
+               exchange={0: 'none', 1: 'ncclAllGather', 2: 'NVLink peer memory'}[int(eng.lib.f['shard_exchange'](eng.h))],
+               message_bytes_per_rank_per_day=int(eng.lib.f['shard_message_bytes'](eng.h)))
+    ctx.close()
+    return out
 
 
 def main():
@@ -178,11 +326,13 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--replicas', type=int, default=256, help='ensemble members (seeds) per GPU (BASELINE configs[3]: 256 seeds)')
+    ap.add_argument('--workload', default='hus')
+    ap.add_argument('--replicas', type=int, default=256, help='ensemble members (seeds) per GPU (weak scaling)')
+    ap.add_argument('--total-seeds', type=int, default=0, help='seeds in total, split evenly over the GPUs (configs[3] as written: strong scaling)')
     ap.add_argument('--days', type=int, default=180)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-single', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='headline only: no strong-scaling point, synthetic population, single seed')
     ap.add_argument('--dump-daily', default=None, help='write the per-day I_d, E_d (ensemble means) the algorithmic bytes are computed from')
     a = ap.parse_args()
 
@@ -194,139 +344,147 @@ def main():
         run_reference(a, rank, world)
         return
 
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    R, D = a.replicas, a.days
+    from reina_b200 import comm as rcomm
+    D = a.days
     peak_gbs, peak_src = load_peaks()
-    ctx = make_context(R, local, D, seed=1)
+
+    if a.workload == 'synth50m':
+        r = bench_synth(a, rank, world, local, N_SYNTH, D, a.steps, a.warmup)
+        if rank == 0:
+            bytes_run = None
+            out = dict(metric='agent-days/sec (synthetic 50M, population-sharded)', value=r['value'], unit='agent-days/s', n_gpus=world,
+                       steps=a.steps, warmup=a.warmup, ms_per_step=r['ms_per_run'], higher_is_better=True, scaling='strong',
+                       vs_baseline=None, dtype='int32/f32 state, f64 uniforms', data='synthetic',
+                       config=dict(workload='synthetic 50,000,000 agents x %d days (HUS age histogram x 29.66, capacity and imports scaled; '
+                                            'BASELINE configs[4]), ONE population sharded over %d GPU(s)' % (D, world),
+                                   l2='2.6 GB of agent state >> L2'),
+                       e2e=dict(value=r['e2e_value'], unit='agent-days/s'), synth50m=r)
+            print(json.dumps(out), flush=True)
+        return
+
+    spec = workload_spec(a.workload)
+    strong = a.total_seeds > 0
+    if strong and a.total_seeds % world:
+        raise SystemExit('--total-seeds must be a multiple of the number of GPUs')
+    R = a.total_seeds // world if strong else a.replicas
+    ctx = make_context(spec, R, local, D, seed=1)
     eng = ctx._engine
+    comm = rcomm.connect(eng, rank, world)        # NCCL through the engine's own C-ABI; LocalComm for one process
+    N = ctx.n_agents
     G = len(ctx.age_group_labels)
     seed_of = lambda step: 1_000_000 * (rank + 1) + 1000 * step     # fresh seeds every step, distinct per rank
 
-    from reina_b200 import ensemble
-
-    # ---------------- device-resident arm (`value`) and end-to-end arm (`e2e`), same steps ----------------
-    def one_step(step, timed):
-        t0 = time.perf_counter()
-        ctx.reset(seed_of(step))                   # fresh ensemble; device state re-initialised in place
-        h2d = ctx.upload_inputs()                  # contact tables of every mobility epoch, from host memory
-        ctx.run(D)                                 # schedule H2D + 180 simulated days + sync
-        dev_ms = eng.last_step_ms()                # CUDA events around the 180-day run only
-        s1, s2, n = ctx.moments(0, D)              # the step's result: sum / sum of squares of every daily series
-        s1g, s2g, ng = ensemble.reduce_moments(s1, s2, n)      # final reduce over the GPUs (NCCL all-reduce)
-        wall = time.perf_counter() - t0
-        h2d += D * 256                             # sizeof(rb_day_params) per day
-        return dev_ms, wall, s1, h2d, s1.nbytes + s2.nbytes
-
-    for step in range(a.warmup):
-        one_step(step, False)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = eng.launch_count()
-    barrier()
-    dev_ms_total, wall_total = 0.0, 0.0
-    s1 = None
-    for step in range(a.warmup, a.warmup + a.steps):
-        dev_ms, wall, s1, h2d, d2h = one_step(step, True)
-        dev_ms_total += dev_ms
-        wall_total += wall
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = eng.launch_count() - launches0
-    dev_ms_total = max_over_ranks(dev_ms_total)
-    wall_total = max_over_ranks(wall_total)
-
-    agent_days_step = float(N_AGENTS) * D * R * world
-    ms_per_step = dev_ms_total / a.steps
+    res = timed_ensemble(ctx, comm, D, a.steps, a.warmup, seed_of, ClockSampler(local) if rank == 0 else None)
+    agent_days_step = float(N) * D * R * world
+    ms_per_step = res['ms_per_step']
     value = agent_days_step / (ms_per_step / 1e3)
-    e2e_value = agent_days_step / (wall_total / a.steps)
-    alg = algorithmic_bytes(s1, N_AGENTS, R, G)
+    e2e_value = agent_days_step / res['wall_per_step']
+    alg = algorithmic_bytes(res['s1'], N, R, G)
 
     if a.dump_daily and rank == 0:
         with open(a.dump_daily, 'w') as f:
-            json.dump(dict(note='HUS, ensemble means over %d seeds of the last timed step: I_d = infected at the start of day d, '
-                                'E_d = contacts sampled on day d-1 (stats row d); bytes_d = 4 N + 12 I_d + 8 E_d (SURVEY.md 8d)' % R,
-                           agents=N_AGENTS, days=D, I_d=alg['daily_infected'], E_d=alg['daily_contacts']), f)
+            json.dump(dict(note='%s, ensemble means over %d seeds of the last timed step: I_d = infected at the start of day d, '
+                                'E_d = contacts sampled on day d-1 (stats row d); bytes_d = 4 N + 12 I_d + 8 E_d (SURVEY.md 8d)' % (spec['area'], R),
+                           agents=N, days=D, I_d=alg['daily_infected'], E_d=alg['daily_contacts']), f)
 
-    # ---------------- per-kernel device times (one extra run, events around every launch) ----------------
-    ctx.reset(seed_of(a.warmup + a.steps - 1))
-    while len(ctx._plan) < D:
-        ctx._plan_next_day()
-    eng.set_schedule(0, ctx._plan[:D])
-    kms = eng.step_profiled(D)
+    # ---------------- per-kernel device times: production geometry and isolated (two extra runs) ----------------
     knames = ['k_pre', 'k_sweep', 'k_expose', 'k_resolve', 'k_post']
-    ksum = float(kms.sum())
-    sweep_ms = float(kms[1]) / D
-    roof_achieved = alg['sweep'] / D / (sweep_ms / 1e3) / 1e9           # GB/s, algorithmic bytes of one sweep launch
+
+    def prepare():
+        ctx.reset(seed_of(a.warmup + a.steps - 1))
+        while len(ctx._plan) < D:
+            ctx._plan_next_day()
+        eng.set_schedule(0, ctx._plan[:D])
+
+    prepare()
+    t_ms, t_cnt, t_wall = eng.step_timed(D)           # rb_step's groups / streams / grids, events around every launch
+    prepare()
+    iso = eng.step_profiled(D)                        # one kernel at a time, full-wave grids
+    share = t_ms / max(float(t_ms.sum()), 1e-9)
+    dom = int(np.argmax(t_ms))
+    kname = knames[dom]
+    # SURVEY 8(d) per-unit figures x the units one launch processes: sweep 4 B/agent + 12 B/infected agent, expose 8 B/contact
+    nominal = {'k_sweep': alg['sweep'], 'k_expose': alg['expose']}.get(kname, 0.0)
+    # what this design's kernels have to move at least: sweep = 16 B per active-list entry (8 read + 8 written); expose = 2 B of
+    # work item + 4 B of susceptibility word per contact
+    design = {'k_sweep': 16.0 * alg['sum_infected'], 'k_expose': 6.0 * alg['sum_contacts']}.get(kname, 0.0)
+    n_launch = max(int(t_cnt[dom]), 1)
+    avg_ms = float(t_ms[dom]) / n_launch
+    achieved = nominal / n_launch / (avg_ms / 1e3) / 1e9 if avg_ms > 0 else 0.0
+    iso_ms = float(iso[dom]) / D
+    traffic, traffic_src = load_traffic(kname, R, D)
     whole = alg['total'] / (ms_per_step / 1e3) / 1e9
 
     out = dict(
-        metric='agent-days/sec (HUS 1.7M)', value=value, unit='agent-days/s', n_gpus=world, steps=a.steps,
-        warmup=a.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None,
+        metric=metric_name(a.workload), value=value, unit='agent-days/s', n_gpus=world, steps=a.steps,
+        warmup=a.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling='strong' if strong else 'weak', vs_baseline=None,
         dtype='int32/f32 state, f64 uniforms', data='synthetic',
         config=dict(
-            workload='HUS 1,685,983 agents x %d days, default interventions (BASELINE configs[1]), ensemble of %d seeds per GPU '
-                     'advanced by the same launches (configs[3] share)' % (D, R),
-            replicas_per_gpu=R, days=D, agents=N_AGENTS, parallelism='ensemble x%d' % world,
-            l2='inputs larger than L2 (%.1f GB of agent state per GPU)' % (R * N_AGENTS * 36.3 / 1e9) if R > 2 else
+            workload='%s x %d days, ensemble of %d seeds per GPU advanced by the same launches%s'
+                     % (spec['label'], D, R, ' (%d seeds in total, configs[3] as written)' % a.total_seeds if strong else ' (configs[3] share per GPU)'),
+            replicas_per_gpu=R, total_seeds=R * world, days=D, agents=N, parallelism='ensemble x%d' % world,
+            l2='inputs larger than L2 (%.1f GB of agent state per GPU)' % (R * N * 52.3 / 1e9) if R > 2 else
                'single 6.7 MB packed-state array is L2-resident by nature of the workload (180 dependent days)',
         ),
-        e2e=dict(value=e2e_value, unit='agent-days/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                 ms_per_step=1e3 * wall_total / a.steps),
-        gpu_launches=int(launches),
-        clocks=clocks,
-        roofline=dict(bound='hbm', kernel='k_sweep', achieved=roof_achieved, peak=peak_gbs, unit='GB/s',
-                      frac=roof_achieved / peak_gbs, traffic=load_sweep_traffic(R) if D == 180 else None, peak_source=peak_src,
-                      algorithmic_bytes_per_launch=alg['sweep'] / D, avg_launch_ms=sweep_ms,
-                      share_of_step=float(kms[1]) / ksum),
+        e2e=dict(value=e2e_value, unit='agent-days/s', h2d_bytes_per_step=int(res['h2d']), d2h_bytes_per_step=int(res['d2h']),
+                 ms_per_step=1e3 * res['wall_per_step'], ms_over_device=1e3 * res['wall_per_step'] - ms_per_step),
+        gpu_launches=int(res['launches']),
+        clocks=res['clocks'],
+        roofline=dict(bound='hbm', kernel=kname, achieved=achieved, peak=peak_gbs, unit='GB/s', frac=achieved / peak_gbs,
+                      traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
+                      algorithmic_bytes_per_launch=nominal / n_launch, avg_launch_ms=avg_ms, launches=n_launch,
+                      geometry='production: %d replica group(s) on concurrent streams, events around every launch on its own stream; '
+                               'launches of different groups overlap, so a launch shares the GPU' % max(1, n_launch // D),
+                      share_of_step=float(share[dom]),
+                      frac_dram=(traffic / (avg_ms / 1e3) / 1e9 / peak_gbs) if traffic else None,
+                      design_bytes_per_launch=design / n_launch, frac_design=design / n_launch / (avg_ms / 1e3) / 1e9 / peak_gbs if avg_ms > 0 else None,
+                      isolated=dict(avg_launch_ms=iso_ms, note='the same kernel over all %d replicas in ONE full-wave launch with the GPU to itself' % R,
+                                    frac=(nominal / D / (iso_ms / 1e3) / 1e9 / peak_gbs) if iso_ms > 0 else None),
+                      note='algorithmic bytes follow SURVEY.md 8(d), defined against the minimal hot state independently of the layout '
+                           '(sweep 4 B/agent + 12 B/infected, contacts 8 B/contact); the list-based sweep never touches the 4 B/agent of the '
+                           'idle population, hence frac_design (this design\'s own minimum) and frac_dram (measured DRAM bytes) beside it'),
         roofline_whole_run=dict(achieved=whole, peak=peak_gbs, unit='GB/s', frac=whole / peak_gbs,
-                                bytes_per_agent_day=alg['total'] / (float(N_AGENTS) * D * R),
+                                bytes_per_agent_day=alg['total'] / (float(N) * D * R),
                                 mean_infected=alg['mean_infected'], mean_contacts_per_day=alg['mean_contacts']),
-        kernel_ms_per_day={k: float(v) / D for k, v in zip(knames, kms)},
+        kernel_ms_per_day=dict(production={k: float(v) / D for k, v in zip(knames, t_ms)}, production_wall_ms_per_day=t_wall / D,
+                               isolated={k: float(v) / D for k, v in zip(knames, iso)}),
     )
+    ctx.close()
 
+    extras = not a.no_extras and a.workload == 'hus' and not strong
+    # ---------------- configs[3] as written: 256 seeds in total, 256 / N per GPU (strong scaling) ----------------
+    if extras and world > 1 and 256 % world == 0:
+        c2 = make_context(spec, 256 // world, local, D, seed=1)
+        comm2 = rcomm.connect(c2._engine, rank, world, key='strong')
+        r2 = timed_ensemble(c2, comm2, D, max(2, a.steps // 2), 2, seed_of)
+        out['strong_scaling_256_seeds'] = dict(
+            value=float(N) * D * 256 / (r2['ms_per_step'] / 1e3), unit='agent-days/s', total_seeds=256, replicas_per_gpu=256 // world,
+            ms_per_step=r2['ms_per_step'], e2e_value=float(N) * D * 256 / r2['wall_per_step'], scaling='strong')
+        c2.close()
+    # ---------------- configs[4]: the synthetic 50 M population on the same GPUs ----------------
+    if extras:
+        s = bench_synth(a, rank, world, local, N_SYNTH, D, 2, 1)
+        out['synth50m'] = s
     # ---------------- single-seed run of the same configuration (latency-bound, reported beside) ----------------
-    if not a.no_single and rank == 0 and R != 1:
-        ctx.close()
-        c1 = make_context(1, local, D, seed=1)
+    if extras and rank == 0 and R != 1:
+        c1 = make_context(spec, 1, local, D, seed=1)
         for s in range(2):
             c1.reset(50 + s); c1.run(D)
         ms = []
         for s in range(3):
             c1.reset(60 + s); c1.run(D); ms.append(c1._engine.last_step_ms())
-        out['single_seed'] = dict(value=N_AGENTS * D / (np.mean(ms) / 1e3), unit='agent-days/s',
+        out['single_seed'] = dict(value=N * D / (np.mean(ms) / 1e3), unit='agent-days/s',
                                   ms_per_run=float(np.mean(ms)), us_per_day=1e3 * float(np.mean(ms)) / D)
         c1.close()
 
     if rank == 0 and not a.no_cpu_baseline and world == 1:
-        b = cpu_baseline(D, np.array([0]), 1)
+        b = cpu_baseline(spec, N, D, np.array([0]), 1)
         out['cpu_baseline'] = {k: b[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     elif rank == 0:
         out['cpu_baseline'] = None
 
     if rank == 0:
         print(json.dumps(out), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

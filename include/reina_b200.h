@@ -102,7 +102,11 @@ typedef struct rb_day_params {
     int32_t n_vacc;                  /* active vaccination programmes (:548-558) */
     int32_t vacc_nr[RB_MAX_VACC], vacc_min_age[RB_MAX_VACC], vacc_max_age[RB_MAX_VACC];
     int32_t vacc_slot[RB_MAX_VACC];  /* stable programme id */
-    int32_t reserved[4];
+    /* bit i: testing mode was test-with-contact-tracing at the moment import event i was applied (interventions of one
+     * date are applied in list order, main.pyx:2012-2015, and person_infect gives the new case an infectee list only
+     * under contact tracing, :227-233) */
+    int32_t import_traced;
+    int32_t reserved[3];
 } rb_day_params;
 
 /* One agent in canonical (layout-independent) form, for parity tests (struct Person, main.pyx:132-144). */
@@ -186,9 +190,31 @@ int rb_read_available(rb_engine *e, int32_t replica, int32_t *beds_icu);  /* {av
 /* timing of the last rb_step measured with CUDA events on the handle's stream (ms); oracle: wall clock */
 float rb_last_step_ms(rb_engine *e);
 /* Like rb_step, but brackets every kernel with CUDA events and returns the summed device time per kernel
- * (ms_per_kernel[RB_N_KERNELS], order: pre, sweep, expose, resolve, post).  Measurement aid for bench.py. */
+ * (ms_per_kernel[RB_N_KERNELS], order: pre, sweep, expose, resolve, post).  One kernel at a time on one stream with
+ * full-wave grids: what each kernel costs when it has the GPU to itself.  Measurement aid for bench.py. */
 #define RB_N_KERNELS 5
 int rb_step_profiled(rb_engine *e, int32_t n_days, float *ms_per_kernel);
+/* The same measurement in the PRODUCTION launch geometry of rb_step (replica groups on concurrent, staggered streams
+ * with rb_step's grids; kernels launched one by one so that events can sit between them).  ms_per_kernel[k] sums the
+ * event-to-event time of kernel k over launches_per_kernel[k] launches; wall_ms is the whole run.  Launches of different
+ * groups overlap, so the per-kernel sums add up to more than wall_ms.  CUDA library only. */
+int rb_step_timed(rb_engine *e, int32_t n_days, float *ms_per_kernel, int32_t *launches_per_kernel, float *wall_ms);
+/* ---- Ensemble across GPUs (BASELINE configs[3]; replaces the reference's multiprocessing.Pool over seeds,
+ * calc/simulation.py:376-377).  The ensemble shards as independent replicas, one process and one engine per GPU, with no
+ * data-path collective; the only exchange is the final reduce of the daily curves, done here with NCCL on device buffers
+ * (libnccl.so.2 is loaded at run time by these calls only).  rb_comm_init joins the engine to a communicator: rank 0 gets
+ * a 128-byte unique id from rb_shard_unique_id and hands it to the other ranks by any host-side means
+ * (reina_b200/comm.py: a file under /tmp for the ranks of one node).  rb_reduce_moments = rb_read_moments summed over all
+ * ranks (sum, sum of squares and the replica count in ONE ncclAllReduce); rb_comm_allreduce (op 0 sum, 1 max; n = 1 makes
+ * it a barrier) and rb_comm_allgather move small host buffers over the same communicator.  Without a communicator all
+ * of them act on the local engine alone. */
+int rb_comm_init(rb_engine *e, int32_t rank, int32_t nranks, const uint8_t *unique_id128);
+int32_t rb_comm_rank(rb_engine *e);
+int32_t rb_comm_size(rb_engine *e);
+int rb_comm_allreduce(rb_engine *e, double *inout, int64_t n, int32_t op);
+int rb_comm_allgather(rb_engine *e, const void *in, void *out, int64_t bytes_per_rank);
+int rb_reduce_moments(rb_engine *e, int32_t day0, int32_t n, double *sum, double *sumsq, int64_t *n_replicas);
+
 /* ---- Population-sharded mode (BASELINE configs[4]; no reference counterpart: the reference is one process).
  * One process per GPU; every rank creates the same engine (same inputs, seed, schedule, n_replicas = 1) and then joins:
  * rank 0 obtains a 128-byte NCCL unique id with rb_shard_unique_id and hands it to the others by any means; each rank
@@ -219,8 +245,16 @@ int64_t rb_state_bytes(rb_engine *e);
 int rb_save_state(rb_engine *e, void *out, int64_t capacity);
 int rb_load_state(rb_engine *e, const void *in, int64_t n_bytes);
 
+/* Measurement aids of the CUDA library (tools/phase_run.py): flag 9 makes the day-boundary kernels record the cycles
+ * they spend per phase; rb_debug_phase_cycles reads the 16 accumulated counters of one replica.  No effect on results. */
+void rb_debug_flag(rb_engine *e, int32_t flag);
+int rb_debug_phase_cycles(rb_engine *e, int32_t replica, long long *out16);
+
 /* number of kernel launches issued by this handle so far */
 int64_t rb_launch_count(rb_engine *e);
+/* bytes this handle has copied so far on the per-run path: direction 0 = host -> device (counter initialisation, contact
+ * tables, schedule), 1 = device -> host (stats rows, moments, problem words).  bench.py reports their per-step deltas. */
+int64_t rb_copied_bytes(rb_engine *e, int32_t direction);
 const char *rb_last_error(void);
 
 #ifdef __cplusplus

@@ -77,6 +77,7 @@ typedef struct {
     int32_t *queue, n_queue, cap_queue;
     int32_t *newq, n_newq, cap_newq;
     int32_t import_ordinal;
+    int32_t list_on;             /* new cases get an infectee list (contact tracing in force at the moment of infection) */
     int32_t testing_mode;
     float p_detected_anyway, p_successful_tracing;
     int32_t epoch;
@@ -267,7 +268,7 @@ static void person_infect(rb_engine *e, Replica *r, int32_t ti, int32_t src, int
         variant = s->variant;
     }
     t->variant = (uint8_t)variant;
-    if (r->testing_mode == RB_ALL_WITH_SYMPTOMS_CT) {
+    if (r->list_on) {     /* hc.testing_mode == ALL_WITH_SYMPTOMS_CT at the moment of infection, main.pyx:227-233 */
         t->has_list = 1;
         t->infectees = (int32_t *)malloc(sizeof(int32_t) * MAX_INFECTEES);
         t->n_infectees = 0;
@@ -574,7 +575,13 @@ static void iterate_replica(rb_engine *e, int ri) {
     r->beds += dp->beds_delta; r->avail_beds += dp->beds_delta;
     r->icu += dp->icu_delta; r->avail_icu += dp->icu_delta;
     r->import_ordinal = 0;
-    for (int i = 0; i < dp->n_imports; i++) infect_people(e, r, dp->import_amount[i], dp->import_variant[i]);
+    /* interventions of one date are applied in list order (main.pyx:2012-2015): an import sees the testing mode that was
+     * in force when its turn came, which the host recorded per event */
+    for (int i = 0; i < dp->n_imports; i++) {
+        r->list_on = (dp->import_traced >> i) & 1;
+        infect_people(e, r, dp->import_amount[i], dp->import_variant[i]);
+    }
+    r->list_on = r->testing_mode == RB_ALL_WITH_SYMPTOMS_CT;
     /* Population.init_day, main.pyx:1687-1699 */
     memset(r->daily_contacts, 0, sizeof r->daily_contacts);
     memset(r->counts[RB_A_NEW_INFECTIONS], 0, sizeof r->counts[0]);
@@ -635,6 +642,14 @@ int ro_create(const rb_config *cfg, const int32_t *age_counts, const int32_t *gr
     if (tot != cfg->n_agents) { snprintf(g_err, sizeof g_err, "age_counts sum %lld != n_agents %d", (long long)tot, cfg->n_agents); free(e); return 1; }
     memcpy(e->variants, variants, sizeof(rb_variant) * cfg->n_variants);
     for (int i = 0; i < cfg->n_import_classes; i++) { e->import_lo[i] = import_lo[i]; e->import_hi[i] = import_hi[i]; e->import_cum[i] = import_cum[i]; }
+    /* an import class that can be drawn (positive weight, or the last one: the fallback) must hold somebody */
+    for (int i = 0; i < cfg->n_import_classes; i++) {
+        float w = import_cum[i] - (i ? import_cum[i - 1] : 0.0f);
+        if (import_lo[i] < 0 || import_hi[i] >= cfg->n_ages || import_lo[i] > import_hi[i]) { snprintf(g_err, sizeof g_err, "import class %d: bad age band", i); free(e); return 1; }
+        if ((w > 0.0f || i == cfg->n_import_classes - 1) && e->age_start[import_hi[i] + 1] - e->age_start[import_lo[i]] <= 0) {
+            snprintf(g_err, sizeof g_err, "import class %d (ages %d-%d) can be drawn but is empty", i, import_lo[i], import_hi[i]); free(e); return 1;
+        }
+    }
     e->row_len = RB_N_ATTRS * cfg->n_groups + RB_N_SCALARS;
     e->stats = (int32_t *)calloc((size_t)cfg->n_replicas * (cfg->max_days + 1) * e->row_len, sizeof(int32_t));
     e->sched = (rb_day_params *)calloc((size_t)cfg->max_days + 1, sizeof(rb_day_params));
@@ -740,6 +755,21 @@ int ro_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *n_rows, con
         e->tables = (Table *)realloc(e->tables, sizeof(Table) * n);
         memset(e->tables + e->n_tables, 0, sizeof(Table) * (n - e->n_tables));
         e->n_tables = n;
+    }
+    /* a row that can be drawn needs somebody in its contact band (the person index is start + u32 % size; the reference
+     * would divide by zero in get_person_from_age_range, main.pyx:1525-1535) */
+    for (int age = 0; age < e->cfg.n_ages; age++) {
+        if (n_rows[age] < 0 || n_rows[age] > RB_MAX_ROWS) { snprintf(g_err, sizeof g_err, "contact table: n_rows[%d] = %d", age, n_rows[age]); return 1; }
+        if (e->age_start[age + 1] == e->age_start[age]) continue;
+        for (int i = 0; i < n_rows[age]; i++) {
+            int k = age * RB_MAX_ROWS + i;
+            if (age_lo[k] < 0 || age_hi[k] >= e->cfg.n_ages || age_lo[k] > age_hi[k]) { snprintf(g_err, sizeof g_err, "contact table: bad band [%d, %d] (age %d row %d)", age_lo[k], age_hi[k], age, i); return 1; }
+            double p = cum_p[k] - (i ? cum_p[k - 1] : 0.0);
+            if ((p > 0.0 || i == n_rows[age] - 1) && e->age_start[age_hi[k] + 1] - e->age_start[age_lo[k]] <= 0) {
+                snprintf(g_err, sizeof g_err, "contact table: row %d of age %d can be drawn (p = %g) but its contact band [%d, %d] is empty", i, age, p, age_lo[k], age_hi[k]);
+                return 1;
+            }
+        }
     }
     Table *t = &e->tables[epoch];
     for (int age = 0; age < e->cfg.n_ages; age++) {

@@ -68,7 +68,7 @@ class DayParams(C.Structure):
         ('trickle', C.c_int32 * RB_MAX_VARIANTS), ('n_vacc', C.c_int32),
         ('vacc_nr', C.c_int32 * RB_MAX_VACC), ('vacc_min_age', C.c_int32 * RB_MAX_VACC),
         ('vacc_max_age', C.c_int32 * RB_MAX_VACC), ('vacc_slot', C.c_int32 * RB_MAX_VACC),
-        ('reserved', C.c_int32 * 4),
+        ('import_traced', C.c_int32), ('reserved', C.c_int32 * 3),
     ]
 
 
@@ -90,7 +90,10 @@ SYMBOLS = ['create', 'destroy', 'reset', 'set_initial_state', 'step_profiled', '
 # population-sharded mode: exported by the CUDA library only (the sequential CPU oracle has no ranks)
 SHARD_SYMBOLS = ['shard_unique_id', 'shard_init', 'shard_rank', 'shard_nranks', 'shard_message_bytes', 'shard_exchange',
                  # checkpoint / resume of the device-resident state
-                 'state_bytes', 'save_state', 'load_state']
+                 'state_bytes', 'save_state', 'load_state',
+                 # ensemble communicator (NCCL), production-geometry timing, measurement aids
+                 'comm_init', 'comm_rank', 'comm_size', 'comm_allreduce', 'comm_allgather', 'reduce_moments',
+                 'step_timed', 'debug_flag', 'debug_phase_cycles', 'copied_bytes']
 SH_SHIFT = 12      # ownership stripes of 4096 agents, dealt round-robin over the ranks (engine.cu owns())
 
 
@@ -169,6 +172,18 @@ class Library:
             f['state_bytes'].restype = C.c_int64
             f['save_state'].argtypes = [vp, C.c_void_p, C.c_int64]
             f['load_state'].argtypes = [vp, C.c_void_p, C.c_int64]
+            f['comm_init'].argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
+            f['comm_rank'].argtypes = [vp]
+            f['comm_size'].argtypes = [vp]
+            f['comm_allreduce'].argtypes = [vp, C.POINTER(C.c_double), C.c_int64, C.c_int32]
+            f['comm_allgather'].argtypes = [vp, C.c_void_p, C.c_void_p, C.c_int64]
+            f['reduce_moments'].argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+            f['step_timed'].argtypes = [vp, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+            f['debug_flag'].argtypes = [vp, C.c_int32]
+            f['debug_flag'].restype = None
+            f['debug_phase_cycles'].argtypes = [vp, C.c_int32, C.c_void_p]
+            f['copied_bytes'].argtypes = [vp, C.c_int32]
+            f['copied_bytes'].restype = C.c_int64
         self.f = f
 
     def check(self, rc, what):
@@ -265,6 +280,44 @@ class Engine:
         self.lib.check(self.lib.f['step_profiled'](self.h, n, _ptr(out, C.c_float)), 'step_profiled')
         return out
 
+    def step_timed(self, n):
+        """rb_step in its production launch geometry with events around every launch: (ms per kernel summed over its
+        launches, launches per kernel, wall ms)."""
+        ms = np.zeros(5, dtype=np.float32)
+        cnt = np.zeros(5, dtype=np.int32)
+        wall = C.c_float()
+        self.lib.check(self.lib.f['step_timed'](self.h, n, _ptr(ms, C.c_float), _ptr(cnt, C.c_int32), C.byref(wall)), 'step_timed')
+        return ms, cnt, float(wall.value)
+
+    # -- NCCL communicator over the engine handle (CUDA library only) --------------------------------------------
+    def comm_init(self, rank, nranks, unique_id):
+        assert len(unique_id) == 128
+        self.lib.check(self.lib.f['comm_init'](self.h, rank, nranks, bytes(unique_id)), 'comm_init')
+        self.rank, self.nranks = rank, nranks
+
+    def comm_allreduce(self, x, op='sum'):
+        a = np.ascontiguousarray(x, dtype=np.float64).copy()
+        self.lib.check(self.lib.f['comm_allreduce'](self.h, _ptr(a, C.c_double), a.size, {'sum': 0, 'max': 1}[op]), 'comm_allreduce')
+        return a
+
+    def comm_allgather(self, x):
+        a = np.ascontiguousarray(x)
+        n = self.lib.f['comm_size'](self.h) if 'comm_size' in self.lib.f else 1
+        out = np.empty((n,) + a.shape, dtype=a.dtype)
+        self.lib.check(self.lib.f['comm_allgather'](self.h, a.ctypes.data, out.ctypes.data, a.nbytes), 'comm_allgather')
+        return out
+
+    def reduce_moments(self, day0, n):
+        """read_moments summed over the ranks of the communicator: (sum, sumsq, total number of replicas)."""
+        s1 = np.empty((n, self.row_len), dtype=np.float64)
+        s2 = np.empty((n, self.row_len), dtype=np.float64)
+        if 'reduce_moments' not in self.lib.f:           # the sequential CPU oracle has no ranks
+            s1, s2 = self.read_moments(day0, n)
+            return s1, s2, self.n_replicas
+        tot = C.c_int64()
+        self.lib.check(self.lib.f['reduce_moments'](self.h, day0, n, _ptr(s1, C.c_double), _ptr(s2, C.c_double), C.byref(tot)), 'reduce_moments')
+        return s1, s2, int(tot.value)
+
     def sync(self):
         self.lib.check(self.lib.f['sync'](self.h), 'sync')
 
@@ -322,6 +375,11 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.f['launch_count'](self.h))
+
+    def copied_bytes(self):
+        """(host -> device, device -> host) bytes copied by this handle so far."""
+        f = self.lib.f['copied_bytes']
+        return int(f(self.h, 0)), int(f(self.h, 1))
 
 
 def shard_unique_id(lib=None):

@@ -296,7 +296,7 @@ __device__ __forceinline__ int32_t import_draw(const Eng &G, const RepCtr *c, si
     int32_t pi = s + (int32_t)(x.y % (uint32_t)(en - s));
     return H_STATE(G.hot[base + pi]) == RB_SUSCEPTIBLE ? pi : -1;
 }
-__device__ void import_infections(const Eng &G, int r, RepCtr *c, int count, int variant, int *ordinal, int32_t *chosen /*[IMP_CHUNK]*/,
+__device__ void import_infections(const Eng &G, int r, RepCtr *c, int count, int variant, bool has_list, int *ordinal, int32_t *chosen /*[IMP_CHUNK]*/,
                                   int *dup_flag) {
     const size_t base = (size_t)r * G.Npad;
     const int tid = threadIdx.x;
@@ -328,7 +328,8 @@ __device__ void import_infections(const Eng &G, int r, RepCtr *c, int count, int
             }
         }
         __syncthreads();
-        if (tid < m && chosen[tid] >= 0) device_infect(G, r, c, chosen[tid], -1, 0u, variant, 0, true);
+        // imported before today's sweep: the new entry goes to the list the sweep is about to read, flagged `fresh`
+        if (tid < m && chosen[tid] >= 0) device_infect(G, r, c, chosen[tid], -1, 0u, variant, 0, true, (int)c->lsel, has_list);
     }
     __syncthreads();
     *ordinal += count;
@@ -400,6 +401,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S, Team &T) {
         // apply_intervention effects dated today (main.pyx:1880-1960), then Population.init_day (:1687-1699)
         if (tid == 0) {
             c->testing_mode = dp->testing_mode;
+            if (dp->testing_mode == RB_ALL_WITH_SYMPTOMS_CT) c->ct_ever = 1u;
             c->p_detected_anyway = dp->p_detected_anyway;
             c->p_successful_tracing = dp->p_successful_tracing;
             c->beds += dp->beds_delta; c->avail_beds += dp->beds_delta;
@@ -407,8 +409,8 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S, Team &T) {
         }
         __syncthreads();
         int ordinal = 0;       // uniform across the CTA
-        for (int i = 0; i < dp->n_imports; i++)
-            import_infections(G, r, c, dp->import_amount[i], dp->import_variant[i], &ordinal, sv, &sh_i[2]);
+        for (int i = 0; i < dp->n_imports; i++)      // in list order; each sees the testing mode in force at its turn (main.pyx:2012-2015)
+            import_infections(G, r, c, dp->import_amount[i], dp->import_variant[i], (dp->import_traced >> i) & 1, &ordinal, sv, &sh_i[2]);
         __syncthreads();
         for (int i = tid; i < G.n_ages; i += blockDim.x) { c->counts[RB_A_NEW_INFECTIONS][i] = 0; c->counts[RB_A_DETECTED][i] = 0; }
         if (tid < RB_N_PLACES) c->daily_contacts[tid] = 0;
@@ -416,7 +418,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S, Team &T) {
         __syncthreads();
         if (tid == 0) { c->epoch = dp->table_epoch; c->total_infectors = 0; c->total_infections = 0; c->exposed_per_day = 0; }
         for (int v = 0; v < G.n_variants; v++)
-            if (dp->trickle[v]) import_infections(G, r, c, dp->trickle[v], v, &ordinal, sv, &sh_i[2]);
+            if (dp->trickle[v]) import_infections(G, r, c, dp->trickle[v], v, dp->testing_mode == RB_ALL_WITH_SYMPTOMS_CT, &ordinal, sv, &sh_i[2]);
         __syncthreads();
         TS(1);   // imports + init_day
         if (tid == 0) { c->ct_cases = (int32_t)nq; c->n_newq = 0; c->n_l0 = 0; c->n_l1 = 0; c->n_edges = 0; }
@@ -442,6 +444,7 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S, Team &T) {
         uint32_t h = G.hot[base + a];
         if (h & H_DET) set_problem(c, RB_WRONG_STATE);   // person_detect, main.pyx:294-298
         G.hot[base + a] = (h & ~H_QUEUED) | H_DET;
+        mark_detected(G, r, a);
         int age = age_of(G, a);
         count_add(c, RB_A_DETECTED, age, 1); count_add(c, RB_A_ALL_DETECTED, age, 1);
     }
@@ -590,10 +593,6 @@ __device__ void pre_body(const Eng &G, const int r, SmemSmall &S, Team &T) {
         c->start = x.x % (uint32_t)G.N;
         c->n_items = 0; c->n_succ = 0; c->n_events = 0;
         c->n_queue_prev = nq;      // tomorrow's queue holds tracing keys whose rank field is < nq
-        // dense days (> 1/24 of the agents infected) stream the packed words, sparse days walk the activity bitmap
-        int infected = 0;
-        for (int age = 0; age < G.n_ages; age++) infected += c->counts[RB_A_INFECTED][age];
-        c->stream_mode = (long long)infected * SW_STREAM_DIV > (long long)G.N ? 1u : 0u;
         c->n_q_base = c->n_newq;
     }
     if (G.xbuf) {     // this rank's message header: the sweep and the contact kernel add to it from zero
@@ -723,6 +722,10 @@ __device__ void post_body(const Eng &G, const int r, SmemSmall &S, Team &T) {
         c->qsel ^= 1u;
         c->n_queue = min(n_newq, G.cap_queue);
         c->n_newq = 0;
+        // the list today's sweep and k_resolve wrote becomes tomorrow's; the one just read is emptied for tomorrow's sweep
+        const uint32_t old = c->lsel;
+        c->lsel = old ^ 1u;
+        c->n_list[old] = 0u;
         c->day = day + 1;            // main.pyx:2009
     }
 }

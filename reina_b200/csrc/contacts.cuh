@@ -108,18 +108,28 @@ __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
         }
         const int nrows = tb->n_rows[age];
         const uint32_t *cum24 = tb->cum24[age];
+        const uint16_t *guide = tb->guide[age];
 #pragma unroll
         for (uint32_t w = 0; w < 4; w++) {
             bool pass = false;
             uint32_t row = 0;
             if (w < ncnt) {
                 const uint32_t word = words[w];
-                // u = (word >> 8) / 2^24; linear scan for the first row with u < cum_p, as an integer compare against
-                // ceil(cum_p 2^24); rows below guide[u's top 10 bits] cannot match
+                // get_one_contact (main.pyx:1290-1304): u = (word >> 8) / 2^24, the row is the first one with u < cum_p, as an
+                // integer compare against ceil(cum_p 2^24).  The guide answers from u's top bits alone for a cell that
+                // lies inside one row; a cell with one boundary costs one compare; the rest walk on from the cell's first row.
                 const uint32_t k24 = word >> 8;
-                row = tb->guide[age][word >> 22];
-                while ((int)row < nrows - 1 && !(k24 < cum24[row])) row++;   // last row on overrun: the reference fails there (p ~ 1e-15)
-                places += 1u << (5 * tb->place[age][row]);               // daily_contacts[place]++ (main.pyx:1571)
+                const uint32_t g = __ldg(&guide[k24 >> (24 - GUIDE_BITS)]);
+                row = g & 127u;
+                uint32_t place = (g >> 7) & 7u;
+                if (g >> 14) {
+                    if (!(k24 < __ldg(&cum24[row]))) {
+                        if ((g >> 14) == 1u) row += (g >> 10) & 15u;
+                        else { row++; while ((int)row < nrows - 1 && !(k24 < __ldg(&cum24[row]))) row++; }   // last row on overrun: the reference fails there (p ~ 1e-15)
+                        place = tb->place[age][row];
+                    }
+                }
+                places += 1u << (5 * place);                              // daily_contacts[place]++ (main.pyx:1571)
                 pass = (int)(word & 255u) < kq;
             }
             const unsigned m = __ballot_sync(0xffffffffu, pass);
@@ -162,7 +172,9 @@ __global__ void __launch_bounds__(256) k_resolve(Eng G) {
         const unsigned long long w = G.rec[base + at.cand].winner;
         const uint32_t src_h = G.hot[base + at.parent];       // in flight together with the conflict slot
         if (w != at.key) continue;                             // first infector in sweep order wins
-        device_infect(G, r, c, (int32_t)at.cand, (int32_t)at.parent, src_h, 0, (int)(at.key & 127ull), false);
+        // infected during today's sweep: first visited tomorrow, so the entry goes to the list today's sweep has written
+        device_infect(G, r, c, (int32_t)at.cand, (int32_t)at.parent, src_h, 0, (int)(at.key & 127ull), false, (int)(c->lsel ^ 1u),
+                      c->testing_mode == RB_ALL_WITH_SYMPTOMS_CT);
         G.rec[base + at.cand].winner = KEY_IDLE;
     }
     // verdict for the day boundary that follows: enough capacity events or queued tests to be worth a team of CTAs
@@ -176,6 +188,7 @@ __global__ void __launch_bounds__(256) k_resolve(Eng G) {
             const uint32_t h = G.hot[base + a];
             if (h & H_DET) set_problem(c, RB_WRONG_STATE);   // person_detect, main.pyx:294-298
             G.hot[base + a] = (h & ~H_QUEUED) | H_DET;
+            mark_detected(G, r, a);
             atomicAdd(&c->drain_det[age_of(G, a)], 1);
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) c->drained = 1u;

@@ -49,12 +49,16 @@ struct rb_engine {
     DevTable **d_tables;
     int n_table_slots;
     rb_day_params *d_sched;
+    double *d_moments;                  // [2][max_days + 1][row_len] + 1: ensemble moments (rb_read_moments / rb_reduce_moments)
+    DevTable *h_stage; int n_stage;     // pinned staging ring for contact-table uploads
+    cudaEvent_t ev_stage[4];
     std::vector<rb_day_params> h_sched;
     std::vector<int32_t> age_start, age_counts;
     std::vector<rb_variant> h_variants;
     int32_t day;
     float last_ms;
     int64_t launches;
+    int64_t h2d_bytes, d2h_bytes;       // bytes this handle copied host -> device / device -> host so far (rb_copied_bytes)
     int sweep_blocks, list_blocks, resolve_blocks;
     cudaGraphExec_t graph[2];
     bool have_graphs;
@@ -66,7 +70,9 @@ struct rb_engine {
     int n_groups;
     ReplicaGroup grp[MAX_GROUPS];
     cudaEvent_t ev_fork;
-    ncclComm_t comm;                    // population-sharded mode
+    ncclComm_t comm;                    // NCCL communicator: the ensemble's final reduce (rb_comm_init) or the population-sharded mode
+    int comm_rank, comm_size;
+    bool sharded;                       // rb_shard_init joined this engine into one population-sharded simulation
     bool shard_timing; std::vector<cudaEvent_t> shard_events;
     int n_peer_open;                    // peer buffers mapped through CUDA IPC: ranks [0, n_peer_open) except the own one
     int merge_blocks;
@@ -79,6 +85,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *);
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
     ncclResult_t (*CommDestroy)(ncclComm_t);
     const char *(*GetErrorString)(ncclResult_t);
 };
@@ -93,9 +100,10 @@ static int load_nccl() {
     g_nccl.GetUniqueId = (ncclResult_t(*)(ncclUniqueId *))dlsym(h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (ncclResult_t(*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
     g_nccl.AllGather = (ncclResult_t(*)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.AllReduce = (ncclResult_t(*)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
     g_nccl.CommDestroy = (ncclResult_t(*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char *(*)(ncclResult_t))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy || !g_nccl.GetErrorString) {
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString) {
         snprintf(g_err, sizeof g_err, "libnccl.so.2 lacks a required symbol"); return 1;
     }
     g_nccl.dl = h;
@@ -132,6 +140,7 @@ static int init_counters(rb_engine *e, uint32_t seed) {
         for (int i = 0; i < RB_MAX_VACC; i++) c.vacc_cursor[i] = -2;
     }
     CK(cudaMemcpyAsync(e->G.ctr, hc.data(), sizeof(RepCtr) * R, cudaMemcpyHostToDevice, e->stream));
+    e->h2d_bytes += (int64_t)sizeof(RepCtr) * R;
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -153,6 +162,7 @@ extern "C" void rb_destroy(rb_engine *e) {
     for (int k = 0; k < e->n_peer_open; k++) if (k != e->G.rank && e->G.xpeer[k]) cudaIpcCloseMemHandle(e->G.xpeer[k]);
     if (e->comm) g_nccl.CommDestroy(e->comm);
     for (void *p : e->allocs) cudaFree(p);
+    if (e->h_stage) { cudaFreeHost(e->h_stage); for (int i = 0; i < 4; i++) cudaEventDestroy(e->ev_stage[i]); }
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaStreamDestroy(e->stream);
     delete e;
@@ -172,8 +182,8 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     CK(cudaSetDevice(cfg->device));
     if (const char *s = getenv("RB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(s));   // measurement aid
     rb_engine *e = new rb_engine();
-    e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0; e->have_graphs = false; e->comm = nullptr; e->merge_blocks = 1;
-    e->has_ipc = false; e->n_groups = 1; e->wide_ctas = 1; e->n_peer_open = 0; e->launch_err = cudaSuccess; e->shard_timing = getenv("RB_SHARD_TIMING") != nullptr;
+    e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0; e->h2d_bytes = 0; e->d2h_bytes = 0; e->have_graphs = false; e->comm = nullptr; e->comm_rank = 0; e->comm_size = 1; e->sharded = false; e->merge_blocks = 1;
+    e->has_ipc = false; e->h_stage = nullptr; e->n_stage = 0; e->n_groups = 1; e->wide_ctas = 1; e->n_peer_open = 0; e->launch_err = cudaSuccess; e->shard_timing = getenv("RB_SHARD_TIMING") != nullptr;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     Eng &G = e->G;
@@ -190,19 +200,29 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     for (int a = 0; a < cfg->n_ages; a++) { e->age_start[a] = (int32_t)tot; tot += age_counts[a]; }
     e->age_start[cfg->n_ages] = (int32_t)tot;
     if (tot != N) { snprintf(g_err, sizeof g_err, "age_counts sum %lld != n_agents %d", (long long)tot, N); delete e; return 1; }
+    // an import class that can be drawn (positive weight, or the last one: the fallback) must hold somebody -- the pick is lo + u32 % size
+    for (int i = 0; i < cfg->n_import_classes; i++) {
+        const float w = import_cum[i] - (i ? import_cum[i - 1] : 0.0f);
+        if (import_lo[i] < 0 || import_hi[i] >= cfg->n_ages || import_lo[i] > import_hi[i]) { snprintf(g_err, sizeof g_err, "import class %d: bad age band", i); delete e; return 1; }
+        if ((w > 0.0f || i == cfg->n_import_classes - 1) && e->age_start[import_hi[i] + 1] - e->age_start[import_lo[i]] <= 0) {
+            snprintf(g_err, sizeof g_err, "import class %d (ages %d-%d) can be drawn but is empty", i, import_lo[i], import_hi[i]); delete e; return 1;
+        }
+    }
     float cc = cfg->contact_capacity > 0 ? cfg->contact_capacity : 1.0f;
     G.cap_items = pow2_at_least((uint64_t)((double)N * cc) + 4096);
     G.cap_succ = pow2_at_least((uint64_t)N / 8 + 4096);
     G.cap_events = pow2_at_least((uint64_t)N / 16 + 2048);
     G.cap_queue = pow2_at_least((uint64_t)N / 8 + 2048);
     const size_t RN = (size_t)R * G.Npad;
+    G.cap_list = (uint32_t)G.Npad;                        // an agent is listed at most once
     G.sus_words = ((G.Npad + 31) / 32 + 32 + 3) & ~3;     // multiple of 4 words: the sweep reads the bitmaps 16 bytes at a time
     if (dalloc(e, &G.hot, RN) || dalloc(e, &G.rec, RN) ||
-        dalloc(e, &G.sus, (size_t)R * G.sus_words) || dalloc(e, &G.act, (size_t)R * G.sus_words) || dalloc(e, &G.items, (size_t)R * G.cap_items) || dalloc(e, &G.succ, (size_t)R * G.cap_succ) ||
+        dalloc(e, &G.sus, (size_t)R * G.sus_words) || dalloc(e, &G.det, (size_t)R * G.sus_words) || dalloc(e, &G.alist, (size_t)R * 2 * G.Npad) || dalloc(e, &G.items, (size_t)R * G.cap_items) || dalloc(e, &G.succ, (size_t)R * G.cap_succ) ||
         dalloc(e, &G.ev_key, (size_t)R * G.cap_events) || dalloc(e, &G.ev_agent, (size_t)R * G.cap_events) ||
         dalloc(e, &G.q_key, (size_t)R * 2 * G.cap_queue) || dalloc(e, &G.q_agent, (size_t)R * 2 * G.cap_queue) ||
         dalloc(e, &G.ctr, (size_t)R) || dalloc(e, &G.stats, (size_t)R * (cfg->max_days + 1) * G.row_len) ||
-        dalloc(e, &e->d_sched, (size_t)cfg->max_days + 1)) { rb_destroy(e); return 1; }
+        dalloc(e, &e->d_sched, (size_t)cfg->max_days + 1) ||
+        dalloc(e, &e->d_moments, 2 * ((size_t)cfg->max_days + 1) * G.row_len + 2)) { rb_destroy(e); return 1; }
     G.sched = e->d_sched;
     e->h_sched.assign(cfg->max_days + 1, rb_day_params());
     e->n_table_slots = 1024;
@@ -241,10 +261,10 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     int sms = prop.multiProcessorCount;
     // the sweep fills the GPU exactly once: SW_CTAS_PER_SM resident CTAs per SM, shared out over the replicas (a grid a
     // little larger than one wave would run its tail on a nearly empty GPU)
-    int want = (G.sus_words / 4 + SW_WARPS * 32 - 1) / (SW_WARPS * 32);
+    // (`want`: a CTA per SW_THREADS list entries is the most a replica's active list can ever use)
+    int want = (G.Npad + SW_THREADS - 1) / SW_THREADS;
     int per_rep = sms * SW_CTAS_PER_SM / R; if (per_rep < 1) per_rep = 1;
     e->sweep_blocks = want < per_rep ? want : per_rep; if (e->sweep_blocks < 1) e->sweep_blocks = 1;
-    CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 9 x 24 KB per SM
     e->list_blocks = sms * EX_CTAS_PER_SM / R; if (e->list_blocks < 2) e->list_blocks = 2;
     // k_resolve is a chain of dependent scattered accesses per infection: enough threads for one pass over the day's list
     e->resolve_blocks = (int)((G.N / 128 + 255) / 256); if (e->resolve_blocks < e->list_blocks) e->resolve_blocks = e->list_blocks;
@@ -283,7 +303,7 @@ static int setup_groups(rb_engine *e, int sms) {
     if (ng == 1) return 0;
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     const Eng &G = e->G;
-    const int want = (G.sus_words / 4 + SW_WARPS * 32 - 1) / (SW_WARPS * 32);
+    const int want = (G.Npad + SW_THREADS - 1) / SW_THREADS;
     for (int g = 0; g < ng; g++) {
         ReplicaGroup &q = e->grp[g];
         q.r0 = (int)((long long)R * g / ng); q.R = (int)((long long)R * (g + 1) / ng) - q.r0;
@@ -307,7 +327,11 @@ extern "C" int rb_reset(rb_engine *e, uint32_t seed) {
     e->G.xepoch++;
     if (init_counters(e, seed)) return 1;
     k_init<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G); e->launches++;
-    if (e->has_ipc) { k_initial_state<<<e->G.R, 32, 0, e->stream>>>(e->G, e->ipc); e->launches++; }
+    if (e->has_ipc) {
+        k_initial_state<<<e->G.R, 32, 0, e->stream>>>(e->G, e->ipc);
+        k_rebuild_lists<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G);
+        e->launches += 2;
+    }
     CK(cudaGetLastError());
     return 0;
 }
@@ -319,9 +343,49 @@ extern "C" int rb_set_initial_state(rb_engine *e, const int32_t *ipc7) {
     e->ipc.dead = ipc7[0]; e->ipc.in_icu = ipc7[1]; e->ipc.in_ward = ipc7[2]; e->ipc.confirmed = ipc7[3];
     e->ipc.incubating = ipc7[4]; e->ipc.ill = ipc7[5]; e->ipc.recovered = ipc7[6];
     e->has_ipc = true;
-    k_initial_state<<<e->G.R, 32, 0, e->stream>>>(e->G, e->ipc); e->launches++;
+    k_initial_state<<<e->G.R, 32, 0, e->stream>>>(e->G, e->ipc);
+    k_rebuild_lists<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G);      // the active lists from the packed words
+    e->launches += 2;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// Row guide of one table (DevTable::guide): rowfn(k) = first row r < nrows - 1 with k < cum24[r], else nrows - 1.
+static void build_row_guide(DevTable *h, int n_ages) {
+    const int shift = 24 - GUIDE_BITS;
+    for (int age = 0; age < n_ages; age++) {
+        const int nrows = h->n_rows[age];
+        if (nrows <= 0) continue;
+        const uint32_t *cum = h->cum24[age];
+        auto rowfn = [&](uint32_t k, int from) { int r = from; while (r < nrows - 1 && !(k < cum[r])) r++; return r; };
+        int r0 = 0;                                     // cum24 is non-decreasing: the first row only moves forward
+        for (uint32_t cell = 0; cell < (1u << GUIDE_BITS); cell++) {
+            const uint32_t lo = cell << shift, hi = lo + (1u << shift) - 1u;
+            r0 = rowfn(lo, r0);
+            const int r1 = rowfn(hi, r0);
+            uint32_t kind = 0, delta = 0;
+            if (r1 != r0) {
+                // lo < cum[r0] <= hi: the first boundary inside the cell.  One boundary only <=> its own value already maps to r1.
+                if (rowfn(cum[r0], r0) == r1 && r1 - r0 <= 15) { kind = 1; delta = (uint32_t)(r1 - r0); } else kind = 2;
+            }
+            h->guide[age][cell] = (uint16_t)((uint32_t)r0 | ((uint32_t)h->place[age][r0] << 7) | (delta << 10) | (kind << 14));
+        }
+    }
+}
+
+// A pinned staging buffer for table uploads: four slots used round-robin, each guarded by an event, so a run of uploads
+// (all mobility epochs of a schedule) is queued as asynchronous copies without a host-device synchronisation per table.
+static int stage_slot(rb_engine *e, DevTable **h, int *slot) {
+    if (!e->h_stage) {
+        CK(cudaMallocHost((void **)&e->h_stage, sizeof(DevTable) * 4));
+        for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
+        e->n_stage = 0;
+    }
+    const int k = e->n_stage & 3;
+    if (e->n_stage >= 4) CK(cudaEventSynchronize(e->ev_stage[k]));     // the copy that last used this slot has left it
+    e->n_stage++;
+    *h = e->h_stage + k; *slot = k;
     return 0;
 }
 
@@ -330,7 +394,23 @@ extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *
                                     const float *mask_p, const double *nr_contacts, const double *ncontact_cdf) {
     if (epoch < 0 || epoch >= e->n_table_slots) { snprintf(g_err, sizeof g_err, "table epoch out of range"); return 1; }
     CK(cudaSetDevice(e->cfg.device));
-    DevTable *h = new DevTable();
+    // a row that can be drawn must have somebody in its contact band: the target index is start + u32 % size
+    for (int age = 0; age < e->cfg.n_ages; age++) {
+        if (n_rows[age] < 0 || n_rows[age] > RB_MAX_ROWS) { snprintf(g_err, sizeof g_err, "contact table: n_rows[%d] = %d", age, n_rows[age]); return 1; }
+        if (e->age_counts[age] == 0) continue;                     // nobody of this age: its rows are never used
+        for (int i = 0; i < n_rows[age]; i++) {
+            const int k = age * RB_MAX_ROWS + i;
+            if (age_lo[k] < 0 || age_hi[k] >= e->cfg.n_ages || age_lo[k] > age_hi[k]) { snprintf(g_err, sizeof g_err, "contact table: bad band [%d, %d] (age %d row %d)", age_lo[k], age_hi[k], age, i); return 1; }
+            const double p = cum_p[k] - (i ? cum_p[k - 1] : 0.0);
+            const bool last = i == n_rows[age] - 1;                  // the fallback row of the search
+            if ((p > 0.0 || last) && e->age_start[age_hi[k] + 1] - e->age_start[age_lo[k]] <= 0) {
+                snprintf(g_err, sizeof g_err, "contact table: row %d of age %d can be drawn (p = %g) but its contact band [%d, %d] is empty", i, age, p, age_lo[k], age_hi[k]);
+                return 1;
+            }
+        }
+    }
+    DevTable *h; int slot;
+    if (stage_slot(e, &h, &slot)) return 1;
     memset(h, 0, sizeof *h);
     for (int age = 0; age < e->cfg.n_ages; age++) {
         h->n_rows[age] = n_rows[age];
@@ -363,17 +443,17 @@ extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *
                 while (k < limit && !(h->ncdf[age][cls][k] > (double)b / 256.0)) k++;
                 h->nguide[age][cls][b] = (uint8_t)k;
             }
-    for (int age = 0; age < e->cfg.n_ages; age++)
-        for (int b = 0, i = 0; b < 1024; b++) {          // cum_p is non-decreasing: the start row only moves forward
-            while (i < n_rows[age] - 1 && !(h->cum_p[age][i] > (double)b / 1024.0)) i++;
-            h->guide[age][b] = (uint8_t)i;
-        }
+    build_row_guide(h, e->cfg.n_ages);
     DevTable *d = e->tables[epoch];
-    if (!d) { if (dalloc(e, &d, 1)) { delete h; return 1; } e->tables[epoch] = d; }
-    CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy(d, h, sizeof(DevTable), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(e->d_tables + epoch, &d, sizeof(DevTable *), cudaMemcpyHostToDevice));
-    delete h;
+    if (!d) {
+        if (dalloc(e, &d, 1)) return 1;
+        e->tables[epoch] = d;
+        CK(cudaMemcpyAsync(e->d_tables + epoch, &e->tables[epoch], sizeof(DevTable *), cudaMemcpyHostToDevice, e->stream));
+    }
+    // stream order keeps the copy behind every kernel of earlier steps (the replica-group streams join e->stream)
+    CK(cudaMemcpyAsync(d, h, sizeof(DevTable), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaEventRecord(e->ev_stage[slot], e->stream));
+    e->h2d_bytes += (int64_t)sizeof(DevTable);
     return 0;
 }
 
@@ -382,6 +462,7 @@ extern "C" int rb_set_schedule(rb_engine *e, int32_t day0, int32_t n, const rb_d
     CK(cudaSetDevice(e->cfg.device));
     memcpy(e->h_sched.data() + day0, params, sizeof(rb_day_params) * n);
     CK(cudaMemcpyAsync(e->d_sched + day0, e->h_sched.data() + day0, sizeof(rb_day_params) * n, cudaMemcpyHostToDevice, e->stream));
+    e->h2d_bytes += (int64_t)sizeof(rb_day_params) * n;
     return 0;
 }
 
@@ -456,6 +537,64 @@ static int build_graphs(rb_engine *e) {
     return 0;
 }
 
+
+// ---------------------------------------------------------------- ensemble communicator (BASELINE configs[3])
+// The Monte-Carlo ensemble shards as independent replicas per GPU; the only exchange is the final reduce of the daily
+// curves.  One process per GPU joins an NCCL communicator through its engine handle (the unique id comes from
+// rb_shard_unique_id and reaches the other ranks by any host-side means), and the reduce runs on device buffers: no
+// other framework is involved.
+extern "C" int rb_comm_init(rb_engine *e, int32_t rank, int32_t nranks, const uint8_t *uid128) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) { snprintf(g_err, sizeof g_err, "bad rank %d / %d", rank, nranks); return 1; }
+    if (e->comm) { snprintf(g_err, sizeof g_err, "rb_comm_init: this engine already has a communicator"); return 1; }
+    if (load_nccl()) return 1;
+    CK(cudaSetDevice(e->cfg.device));
+    ncclUniqueId id; memcpy(&id, uid128, 128);
+    NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
+    e->comm_rank = rank; e->comm_size = nranks;
+    return 0;
+}
+extern "C" int32_t rb_comm_rank(rb_engine *e) { return e->comm_rank; }
+extern "C" int32_t rb_comm_size(rb_engine *e) { return e->comm_size; }
+
+// scratch on the device for host-buffer collectives: the moments buffer if it is large enough, else a temporary
+static int comm_scratch(rb_engine *e, size_t bytes, void **p, bool *temp) {
+    const size_t have = sizeof(double) * (2 * ((size_t)e->cfg.max_days + 1) * e->G.row_len + 2);
+    if (bytes <= have) { *p = e->d_moments; *temp = false; return 0; }
+    CK(cudaMalloc(p, bytes)); *temp = true;
+    return 0;
+}
+
+// In-place all-reduce of n doubles held by the host.  op: 0 = sum, 1 = max.  Doubles as a barrier (n = 1).
+extern "C" int rb_comm_allreduce(rb_engine *e, double *inout, int64_t n, int32_t op) {
+    if (n < 0 || (op != 0 && op != 1)) { snprintf(g_err, sizeof g_err, "rb_comm_allreduce: bad arguments"); return 1; }
+    if (!e->comm || e->comm_size == 1 || n == 0) return 0;
+    CK(cudaSetDevice(e->cfg.device));
+    void *d; bool temp;
+    if (comm_scratch(e, sizeof(double) * (size_t)n, &d, &temp)) return 1;
+    CK(cudaMemcpyAsync(d, inout, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    NK(g_nccl.AllReduce(d, d, (size_t)n, ncclDouble, op == 0 ? ncclSum : ncclMax, e->comm, e->stream));
+    CK(cudaMemcpyAsync(inout, d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (temp) cudaFree(d);
+    return 0;
+}
+
+// All-gather of `bytes` bytes per rank between host buffers: out[rank k] = in of rank k.
+extern "C" int rb_comm_allgather(rb_engine *e, const void *in, void *out, int64_t bytes) {
+    if (bytes < 0) { snprintf(g_err, sizeof g_err, "rb_comm_allgather: bad size"); return 1; }
+    if (!e->comm || e->comm_size == 1) { memcpy(out, in, (size_t)bytes); return 0; }
+    CK(cudaSetDevice(e->cfg.device));
+    void *d; bool temp;
+    if (comm_scratch(e, (size_t)bytes * e->comm_size, &d, &temp)) return 1;
+    uint8_t *mine = (uint8_t *)d + (size_t)bytes * e->comm_rank;
+    CK(cudaMemcpyAsync(mine, in, (size_t)bytes, cudaMemcpyHostToDevice, e->stream));
+    NK(g_nccl.AllGather(mine, d, (size_t)bytes, ncclChar, e->comm, e->stream));
+    CK(cudaMemcpyAsync(out, d, (size_t)bytes * e->comm_size, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (temp) cudaFree(d);
+    return 0;
+}
+
 // ---------------------------------------------------------------- population-sharded mode
 extern "C" int rb_shard_unique_id(uint8_t *out128) {
     if (load_nccl()) return 1;
@@ -474,6 +613,7 @@ extern "C" int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const u
     CK(cudaSetDevice(e->cfg.device));
     ncclUniqueId id; memcpy(&id, uid128, 128);
     NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
+    e->comm_rank = rank; e->comm_size = nranks; e->sharded = true;
     Eng &G = e->G;
     // message capacities: this rank's share of the agents; a day's state changes / transmissions / tests / capacity
     // events are small fractions of it (peak day of the reference epidemic: 0.9 % / 0.5 % / 0.17 % / 0.08 % of the
@@ -537,19 +677,15 @@ extern "C" int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const u
         }
     }
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, e->cfg.device));
-    {   // a rank walks 1 / nranks of the activity bitmap, with the whole GPU: one wave unless there are fewer warp steps than that
-        const int want = ((G.sus_words / 4 + 31) / 32 + nranks - 1) / nranks;           // this rank's warp steps
-        int sb = (want + SW_WARPS - 1) / SW_WARPS; if (sb < 1) sb = 1;
-        if (sb < e->sweep_blocks) e->sweep_blocks = sb;
-    }
+    // (the sweep needs no adjustment: a rank's active list holds only the agents it owns, ~1 / nranks of the infected)
     e->merge_blocks = prop.multiProcessorCount * 8 / nranks * nranks;      // a multiple of nranks: k_merge deals its blocks to the ranks
     return 0;
 }
 
 extern "C" int32_t rb_shard_rank(rb_engine *e) { return e->G.rank; }
 extern "C" int32_t rb_shard_nranks(rb_engine *e) { return e->G.nranks; }
-extern "C" int64_t rb_shard_message_bytes(rb_engine *e) { return e->comm ? (int64_t)e->G.xslot : 0; }
-extern "C" int32_t rb_shard_exchange(rb_engine *e) { return !e->comm ? 0 : (e->G.xp2p ? 2 : 1); }
+extern "C" int64_t rb_shard_message_bytes(rb_engine *e) { return e->sharded ? (int64_t)e->G.xslot : 0; }
+extern "C" int32_t rb_shard_exchange(rb_engine *e) { return !e->sharded ? 0 : (e->G.xp2p ? 2 : 1); }
 
 // One simulated day in sharded mode: sweep and contacts over the owned stripes, ONE all-gather of the ranks' messages,
 // then merge / resolve / day boundary replicated on every rank.
@@ -576,24 +712,39 @@ static int launch_day_sharded(rb_engine *e, bool last) {
     return 0;
 }
 
-extern "C" int rb_step(rb_engine *e, int32_t n_days) {
-    CK(cudaSetDevice(e->cfg.device));
-    if (n_days <= 0) return 0;
+// what every stepping entry point checks first: the range of days and that each day's contact table was uploaded
+static int check_days(rb_engine *e, int32_t n_days) {
+    if (n_days < 0) { snprintf(g_err, sizeof g_err, "negative number of days"); return 1; }
     if (e->day + n_days > e->cfg.max_days) { snprintf(g_err, sizeof g_err, "max_days exceeded"); return 1; }
     for (int d = 0; d < n_days; d++) {
         int ep = e->h_sched[e->day + d].table_epoch;
         if (ep < 0 || ep >= e->n_table_slots || !e->tables[ep]) { snprintf(g_err, sizeof g_err, "contact table %d not set", ep); return 1; }
     }
-    if (!e->comm && !e->have_graphs && build_graphs(e)) return 1;
+    return 0;
+}
+static int check_launches(rb_engine *e) {
+    CK(cudaGetLastError());
+    if (e->launch_err != cudaSuccess) {
+        snprintf(g_err, sizeof g_err, "cooperative launch of the day boundary failed: %s", cudaGetErrorString(e->launch_err));
+        e->launch_err = cudaSuccess;
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" int rb_step(rb_engine *e, int32_t n_days) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (check_days(e, n_days)) return 1;
+    if (n_days == 0) return 0;
+    if (!e->sharded && !e->have_graphs && build_graphs(e)) return 1;
     const Eng &G = e->G;
     const int R = G.R;
-    if (e->comm) {
+    if (e->sharded) {
         CK(cudaEventRecord(e->ev0, e->stream));
         launch_boundary(e, 0, 1, e->stream, G); e->launches++;
         for (int d = 0; d < n_days; d++) if (launch_day_sharded(e, d == n_days - 1)) return 1;
         CK(cudaEventRecord(e->ev1, e->stream));
-        CK(cudaGetLastError());
-        if (e->launch_err != cudaSuccess) { snprintf(g_err, sizeof g_err, "cooperative launch of the day boundary failed: %s", cudaGetErrorString(e->launch_err)); return 1; }
+        if (check_launches(e)) return 1;
         e->day += n_days;
         return 0;
     }
@@ -619,8 +770,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
             CK(cudaStreamWaitEvent(e->stream, q.ev_join, 0));
         }
         CK(cudaEventRecord(e->ev1, e->stream));
-        CK(cudaGetLastError());
-        if (e->launch_err != cudaSuccess) { snprintf(g_err, sizeof g_err, "cooperative launch of the day boundary failed: %s", cudaGetErrorString(e->launch_err)); return 1; }
+        if (check_launches(e)) return 1;
         e->day += n_days;
         return 0;
     }
@@ -635,16 +785,19 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     launch_boundary(e, 1, R, e->stream, G);
     e->launches += 4;
     CK(cudaEventRecord(e->ev1, e->stream));
-    CK(cudaGetLastError());
-    if (e->launch_err != cudaSuccess) { snprintf(g_err, sizeof g_err, "cooperative launch of the day boundary failed: %s", cudaGetErrorString(e->launch_err)); return 1; }
+    if (check_launches(e)) return 1;
     e->day += n_days;
     return 0;
 }
 
+// rb_step with CUDA events around every launch, one kernel at a time on ONE stream with full-wave grids (no replica
+// groups, no graphs): what each kernel costs when it has the GPU to itself.
 extern "C" int rb_step_profiled(rb_engine *e, int32_t n_days, float *ms_per_kernel) {
     CK(cudaSetDevice(e->cfg.device));
-    if (e->day + n_days > e->cfg.max_days) { snprintf(g_err, sizeof g_err, "max_days exceeded"); return 1; }
-    if (e->comm) { snprintf(g_err, sizeof g_err, "rb_step_profiled: not available in population-sharded mode"); return 1; }
+    if (e->sharded) { snprintf(g_err, sizeof g_err, "rb_step_profiled: not available in population-sharded mode"); return 1; }
+    if (check_days(e, n_days)) return 1;
+    for (int k = 0; k < RB_N_KERNELS; k++) ms_per_kernel[k] = 0;
+    if (n_days == 0) return 0;
     const Eng &G = e->G;
     const int R = G.R;
     std::vector<cudaEvent_t> ev((size_t)n_days * 6);
@@ -659,12 +812,80 @@ extern "C" int rb_step_profiled(rb_engine *e, int32_t n_days, float *ms_per_kern
         launch_boundary(e, 1, R, e->stream, G); CK(cudaEventRecord(v[5], e->stream));
         e->launches += 5;
     }
-    CK(cudaGetLastError());
+    const int bad = check_launches(e);
     CK(cudaStreamSynchronize(e->stream));
-    for (int k = 0; k < RB_N_KERNELS; k++) ms_per_kernel[k] = 0;
-    for (int d = 0; d < n_days; d++)
-        for (int k = 0; k < RB_N_KERNELS; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ev[(size_t)d * 6 + k], ev[(size_t)d * 6 + k + 1])); ms_per_kernel[k] += ms; }
+    if (!bad)
+        for (int d = 0; d < n_days; d++)
+            for (int k = 0; k < RB_N_KERNELS; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ev[(size_t)d * 6 + k], ev[(size_t)d * 6 + k + 1])); ms_per_kernel[k] += ms; }
     for (auto &x : ev) cudaEventDestroy(x);
+    if (bad) return 1;
+    e->day += n_days;
+    return 0;
+}
+
+// The PRODUCTION launch geometry of rb_step -- the replica groups on their concurrent streams, staggered, with the
+// grids rb_step uses -- with CUDA events around every launch on the stream it is launched on (kernels are launched one
+// by one instead of from graphs so that events can sit between them).  ms_per_kernel[k] sums the event-to-event time of
+// kernel k over all its launches, launches_per_kernel[k] counts them (order: pre, sweep, expose, resolve, post/between);
+// wall_ms is the whole run.  With several groups the launches of different groups overlap, so the sum of all kernel times
+// exceeds wall_ms: a launch's duration here is what it takes WHILE sharing the GPU with the other groups' kernels.
+extern "C" int rb_step_timed(rb_engine *e, int32_t n_days, float *ms_per_kernel, int32_t *launches_per_kernel, float *wall_ms) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->sharded) { snprintf(g_err, sizeof g_err, "rb_step_timed: not available in population-sharded mode"); return 1; }
+    if (check_days(e, n_days)) return 1;
+    for (int k = 0; k < RB_N_KERNELS; k++) { ms_per_kernel[k] = 0; launches_per_kernel[k] = 0; }
+    *wall_ms = 0;
+    if (n_days == 0) return 0;
+    const Eng &G = e->G;
+    const int R = G.R;
+    struct Span { cudaEvent_t a, b; int k; };
+    std::vector<Span> spans;
+    auto mark = [&](cudaStream_t st) { cudaEvent_t x; cudaEventCreate(&x); cudaEventRecord(x, st); return x; };
+    // one group without streams of its own when the engine runs ungrouped
+    ReplicaGroup whole; whole.r0 = 0; whole.R = R; whole.sweep_blocks = e->sweep_blocks; whole.list_blocks = e->list_blocks;
+    whole.resolve_blocks = e->resolve_blocks; whole.stream = e->stream;
+    const int ng = e->n_groups > 1 ? e->n_groups : 1;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    { cudaEvent_t a = mark(e->stream); launch_boundary(e, 0, R, e->stream, G); spans.push_back({a, mark(e->stream), 0}); e->launches++; }
+    if (ng > 1) CK(cudaEventRecord(e->ev_fork, e->stream));
+    for (int d = 0; d < n_days; d++) {
+        const bool last = d == n_days - 1;
+        for (int g = 0; g < ng; g++) {
+            ReplicaGroup &q = ng > 1 ? e->grp[g] : whole;
+            if (ng > 1 && d == 0) {
+                CK(cudaStreamWaitEvent(q.stream, e->ev_fork, 0));
+                if (g > 0 && n_days > 1) CK(cudaStreamWaitEvent(q.stream, e->grp[g - 1].ev_stagger, 0));
+            }
+            Eng Gq = G; Gq.r0 = q.r0;
+            cudaEvent_t t0 = mark(q.stream);
+            k_sweep<<<dim3(q.sweep_blocks, q.R), SW_THREADS, 0, q.stream>>>(Gq);
+            cudaEvent_t t1 = mark(q.stream);
+            k_expose<<<dim3(q.list_blocks, q.R), EX_THREADS, 0, q.stream>>>(Gq);
+            cudaEvent_t t2 = mark(q.stream);
+            if (ng > 1 && d == 0 && g + 1 < ng && n_days > 1) CK(cudaEventRecord(q.ev_stagger, q.stream));
+            if (last) k_resolve<false><<<dim3(q.resolve_blocks, q.R), 256, 0, q.stream>>>(Gq);
+            else k_resolve<true><<<dim3(q.resolve_blocks, q.R), 256, 0, q.stream>>>(Gq);
+            cudaEvent_t t3 = mark(q.stream);
+            launch_boundary(e, last ? 1 : 2, q.R, q.stream, Gq);
+            cudaEvent_t t4 = mark(q.stream);
+            spans.push_back({t0, t1, 1}); spans.push_back({t1, t2, 2}); spans.push_back({t2, t3, 3}); spans.push_back({t3, t4, 4});
+            e->launches += 4;
+            if (ng > 1 && last) { CK(cudaEventRecord(q.ev_join, q.stream)); CK(cudaStreamWaitEvent(e->stream, q.ev_join, 0)); }
+        }
+    }
+    CK(cudaEventRecord(e->ev1, e->stream));
+    const int bad = check_launches(e);
+    CK(cudaStreamSynchronize(e->stream));
+    if (!bad) {
+        for (const Span &s : spans) { float ms = 0; CK(cudaEventElapsedTime(&ms, s.a, s.b)); ms_per_kernel[s.k] += ms; launches_per_kernel[s.k]++; }
+        CK(cudaEventElapsedTime(wall_ms, e->ev0, e->ev1));
+    }
+    std::vector<cudaEvent_t> seen;
+    for (const Span &s : spans) { seen.push_back(s.a); seen.push_back(s.b); }
+    std::sort(seen.begin(), seen.end());
+    seen.erase(std::unique(seen.begin(), seen.end()), seen.end());
+    for (cudaEvent_t x : seen) cudaEventDestroy(x);
+    if (bad) return 1;
     e->day += n_days;
     return 0;
 }
@@ -696,6 +917,7 @@ extern "C" int rb_debug_phase_cycles(rb_engine *e, int32_t replica, long long *o
 extern "C" int32_t rb_row_len(rb_engine *e) { return e->G.row_len; }
 extern "C" float rb_last_step_ms(rb_engine *e) { return e->last_ms; }
 extern "C" int64_t rb_launch_count(rb_engine *e) { return e->launches; }
+extern "C" int64_t rb_copied_bytes(rb_engine *e, int32_t direction) { return direction == 0 ? e->h2d_bytes : e->d2h_bytes; }
 
 extern "C" int rb_snapshot(rb_engine *e) {
     CK(cudaSetDevice(e->cfg.device));
@@ -712,6 +934,7 @@ extern "C" int rb_read_stats(rb_engine *e, int32_t day0, int32_t n, int32_t *out
                          G.stats + (size_t)day0 * G.row_len, sizeof(int32_t) * (size_t)(G.max_days + 1) * G.row_len,
                          sizeof(int32_t) * (size_t)n * G.row_len, G.R, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    e->d2h_bytes += (int64_t)sizeof(int32_t) * n * G.row_len * G.R;
     return 0;
 }
 
@@ -719,13 +942,36 @@ extern "C" int rb_read_moments(rb_engine *e, int32_t day0, int32_t n, double *su
     CK(cudaSetDevice(e->cfg.device));
     if (day0 < 0 || n < 1 || day0 + n > e->cfg.max_days + 1) { snprintf(g_err, sizeof g_err, "stats range"); return 1; }
     const size_t cnt = (size_t)n * e->G.row_len;
-    double *d; CK(cudaMalloc(&d, sizeof(double) * 2 * cnt));
+    double *d = e->d_moments;           // allocated once by rb_create for max_days + 1 rows
     k_moments<<<n, 160, 0, e->stream>>>(e->G, day0, d, d + cnt); e->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(sum, d, sizeof(double) * cnt, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(sumsq, d + cnt, sizeof(double) * cnt, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    cudaFree(d);
+    e->d2h_bytes += (int64_t)sizeof(double) * 2 * cnt;
+    return 0;
+}
+
+
+// rb_read_moments over the whole ensemble: the moments of this GPU's replicas are reduced on the device, summed over the
+// communicator's ranks with one ncclAllReduce (sum, sum of squares and the replica count travel together), and only the
+// result crosses to the host.  Without a communicator it is rb_read_moments plus the local replica count.
+extern "C" int rb_reduce_moments(rb_engine *e, int32_t day0, int32_t n, double *sum, double *sumsq, int64_t *n_replicas) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (day0 < 0 || n < 1 || day0 + n > e->cfg.max_days + 1) { snprintf(g_err, sizeof g_err, "stats range"); return 1; }
+    const size_t cnt = (size_t)n * e->G.row_len;
+    double *d = e->d_moments;
+    k_moments<<<n, 160, 0, e->stream>>>(e->G, day0, d, d + cnt); e->launches++;
+    CK(cudaGetLastError());
+    double nrep = (double)e->G.R;
+    CK(cudaMemcpyAsync(d + 2 * cnt, &nrep, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (e->comm && e->comm_size > 1 && !e->sharded) NK(g_nccl.AllReduce(d, d, 2 * cnt + 1, ncclDouble, ncclSum, e->comm, e->stream));
+    CK(cudaMemcpyAsync(sum, d, sizeof(double) * cnt, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(sumsq, d + cnt, sizeof(double) * cnt, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(&nrep, d + 2 * cnt, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->h2d_bytes += 8; e->d2h_bytes += (int64_t)sizeof(double) * (2 * cnt + 1);
+    *n_replicas = (int64_t)(nrep + 0.5);
     return 0;
 }
 
@@ -740,7 +986,9 @@ extern "C" int rb_read_per_age(rb_engine *e, int32_t replica, int32_t attr, int3
 extern "C" int rb_problem(rb_engine *e, int32_t *out) {
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaStreamSynchronize(e->stream));
-    for (int r = 0; r < e->G.R; r++) CK(cudaMemcpy(out + r, &e->G.ctr[r].problem, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    // one strided copy: the problem word of every replica's counter block
+    CK(cudaMemcpy2D(out, sizeof(int32_t), &e->G.ctr[0].problem, sizeof(RepCtr), sizeof(int32_t), (size_t)e->G.R, cudaMemcpyDeviceToHost));
+    e->d2h_bytes += (int64_t)sizeof(int32_t) * e->G.R;
     return 0;
 }
 
@@ -761,6 +1009,9 @@ extern "C" int rb_read_agents(rb_engine *e, int32_t replica, rb_agent *out) {
     CK(cudaSetDevice(e->cfg.device));
     const Eng &G = e->G;
     if (replica < 0 || replica >= G.R) { snprintf(g_err, sizeof g_err, "bad replica"); return 1; }
+    // the current day counters live in the active lists: write them back into the packed words first
+    k_flush_lists<<<dim3(e->sweep_blocks, G.R), 256, 0, e->stream>>>(G); e->launches++;
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     const int N = G.N; const size_t base = (size_t)replica * G.Npad;
     std::vector<uint32_t> hot(N), cold(N); std::vector<int32_t> inf(N); std::vector<int16_t> vd(N);
@@ -813,7 +1064,7 @@ static std::vector<StatePart> state_parts(rb_engine *e) {
     const Eng &G = e->G;
     const size_t RN = (size_t)G.R * G.Npad, RW = (size_t)G.R * G.sus_words, RQ = (size_t)G.R * 2 * G.cap_queue;
     return {
-        {G.hot, RN * sizeof(uint32_t)}, {G.rec, RN * sizeof(AgentRec)}, {G.sus, RW * sizeof(uint32_t)}, {G.act, RW * sizeof(uint32_t)},
+        {G.hot, RN * sizeof(uint32_t)}, {G.rec, RN * sizeof(AgentRec)}, {G.sus, RW * sizeof(uint32_t)}, {G.det, RW * sizeof(uint32_t)},
         {G.ctr, (size_t)G.R * sizeof(RepCtr)}, {G.q_key, RQ * sizeof(unsigned long long)}, {G.q_agent, RQ * sizeof(int32_t)},
         {G.stats, (size_t)G.R * (G.max_days + 1) * G.row_len * sizeof(int32_t)},
     };
@@ -821,7 +1072,7 @@ static std::vector<StatePart> state_parts(rb_engine *e) {
 static StateHeader state_header(rb_engine *e) {
     const Eng &G = e->G;
     StateHeader h; memset(&h, 0, sizeof h);
-    h.magic = STATE_MAGIC; h.version = 1; h.n_agents = G.N; h.n_replicas = G.R; h.n_ages = G.n_ages; h.row_len = G.row_len;
+    h.magic = STATE_MAGIC; h.version = 2; h.n_agents = G.N; h.n_replicas = G.R; h.n_ages = G.n_ages; h.row_len = G.row_len;
     h.max_days = G.max_days; h.day = e->day; h.sus_words = G.sus_words; h.cap_queue = G.cap_queue; h.seed = e->cfg.seed;
     h.rec_bytes = (int32_t)sizeof(AgentRec); h.ctr_bytes = (int32_t)sizeof(RepCtr);
     return h;
@@ -836,6 +1087,10 @@ extern "C" int64_t rb_state_bytes(rb_engine *e) {
 extern "C" int rb_save_state(rb_engine *e, void *out, int64_t capacity) {
     CK(cudaSetDevice(e->cfg.device));
     if (capacity < rb_state_bytes(e)) { snprintf(g_err, sizeof g_err, "rb_save_state: buffer of %lld bytes, need %lld", (long long)capacity, (long long)rb_state_bytes(e)); return 1; }
+    // the active lists are not part of the blob: their day counters are written back into the packed words here and
+    // rb_load_state rebuilds the lists from those
+    k_flush_lists<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G); e->launches++;
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     uint8_t *o = (uint8_t *)out;
     const StateHeader h = state_header(e);
@@ -854,6 +1109,11 @@ extern "C" int rb_load_state(rb_engine *e, const void *in, int64_t n_bytes) {
     CK(cudaStreamSynchronize(e->stream));
     const uint8_t *o = (const uint8_t *)in + sizeof h;
     for (const StatePart &p : state_parts(e)) { CK(cudaMemcpy(p.dev, o, p.bytes, cudaMemcpyHostToDevice)); o += p.bytes; }
+    // both list counters to zero, then list `lsel` of every replica from the packed words
+    CK(cudaMemset2DAsync(&e->G.ctr[0].n_list[0], sizeof(RepCtr), 0, sizeof(uint32_t) * 2, (size_t)e->G.R, e->stream));
+    k_rebuild_lists<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G); e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
     e->day = h.day; e->cfg.seed = h.seed;
     e->G.xepoch++;
     return 0;

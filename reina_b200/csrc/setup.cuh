@@ -79,7 +79,7 @@ __global__ void k_initial_state(Eng G, Ipc P) {
         // a person drawn before is infected again, exactly as the reference does; person_infect (main.pyx:209-235) resets
         // state, severity and the day counter but leaves was_detected alone
         const uint32_t was_detected = G.hot[base + a] & H_DET;
-        device_infect(G, r, c, a, -1, 0u, 0, 0, true);
+        device_infect(G, r, c, a, -1, 0u, 0, 0, true, -1, false);     // no list entry: a person drawn twice must not be listed twice, k_rebuild_lists follows
         if (was_detected) G.hot[base + a] |= H_DET;
         if (i < i_incubating) continue;                              // still incubating: waits one day like any same-day infection
         if (i < i_rws) { init_remove(G, c, base, a, age, false); continue; }
@@ -108,7 +108,7 @@ __global__ void k_init(Eng G) {
         int first = w * 32;
         uint32_t m = first + 32 <= G.N ? 0xffffffffu : (first >= G.N ? 0u : ((1u << (G.N - first)) - 1u));
         G.sus[(size_t)r * G.sus_words + w] = m;
-        G.act[(size_t)r * G.sus_words + w] = 0u;
+        G.det[(size_t)r * G.sus_words + w] = 0u;
     }
 }
 

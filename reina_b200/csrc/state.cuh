@@ -13,14 +13,12 @@
 #include <dlfcn.h>
 #include <nccl.h>      // types only: libnccl is loaded at run time by rb_shard_init, single-GPU use never needs it
 
+#include <algorithm>
 #include <vector>
 
 #include "../../include/reina_b200.h"
 #include "rng.cuh"
 
-#ifndef SW_STREAM_DIV
-#define SW_STREAM_DIV 6      // the sweep streams the packed words once more than 1 / 6 of the agents are infected (measured: the bitmap walk wins below)
-#endif
 #define MAX_INFECTEES 64   // main.pyx:128
 #define MAX_CONTACTS 128   // main.pyx:129
 
@@ -36,6 +34,8 @@
 #define H_VACC (1u << 13)
 #define H_DL(h) (((h) >> 14) & 255u)
 #define H_DOI(h) (((h) >> 22) & 31u)
+#define H_PEND (1u << 27)    // active-list copies only: a bed / ICU claim is pending, the day boundary decides -- reload the word from `hot`
+#define H_DAYS_MASK ((255u << 14) | (31u << 22))     // the two day counters: kept current in the active list, in `hot` only at state changes
 #define H_SET_STATE(h, s) (((h) & ~7u) | (uint32_t)(s))
 #define H_SET_DL(h, d) (((h) & ~(255u << 14)) | ((uint32_t)(d) << 14))
 #define H_SET_DOI(h, d) (((h) & ~(31u << 22)) | ((uint32_t)(d) << 22))
@@ -56,6 +56,9 @@ enum { EV_HOSP_CLAIM = 0, EV_WARD_RELEASE = 1, EV_TO_ICU = 2, EV_ICU_RELEASE = 3
 #endif
 #define NEG_INF (-(1 << 29))
 
+#ifndef GUIDE_BITS
+#define GUIDE_BITS 10        // cells per age in the row guide (2 KB per age: the table of one epoch stays L1-resident)
+#endif
 struct DevTable {
     int32_t n_rows[RB_MAX_AGES];
     float nr_contacts[RB_MAX_AGES];
@@ -68,7 +71,11 @@ struct DevTable {
     uint8_t place[RB_MAX_AGES][RB_MAX_ROWS];
     uint8_t lo_age[RB_MAX_AGES][RB_MAX_ROWS], hi_age[RB_MAX_AGES][RB_MAX_ROWS];
     uint8_t susc_uniform[RB_MAX_AGES][RB_MAX_ROWS];   // susceptibility identical for every age of the row's band
-    uint8_t guide[RB_MAX_AGES][1024];                 // first row whose cum_p exceeds b/1024: start of the row search
+    // O(1) row pick (get_one_contact, main.pyx:1290-1304): the 24-bit uniform's top GUIDE_BITS bits select a cell; the
+    // entry says which row the cell's first value maps to, that row's place, and whether the whole cell maps to it
+    // (kind 0), or everything from cum24[row0] on maps to row0 + delta (kind 1: one boundary inside the cell, rows of zero
+    // probability in between), or the cell holds several boundaries and the search walks on from row0 (kind 2, rare)
+    uint16_t guide[RB_MAX_AGES][1 << GUIDE_BITS];     // row0 7b | place0 3b << 7 | delta 4b << 10 | kind 2b << 14
     uint8_t nguide[RB_MAX_AGES][2][256];              // first k with ncdf[k] > b/256: start of the contact-count search
 };
 
@@ -99,12 +106,14 @@ struct RepCtr {
     uint32_t n_queue, qsel;
     uint32_t n_queue_prev;                        // size of the queue drained yesterday (normalises tracing keys for sorting)
     uint32_t any_vacc;                            // set once the first vaccination programme starts
-    uint32_t stream_mode;                         // today's sweep streams the packed words instead of the activity bitmap
+    uint32_t lsel;                                // active list in force today: the sweep reads list lsel and writes list lsel ^ 1
+    uint32_t ct_ever;                             // contact tracing has been on at some point: detections may reach agents behind the list's back
     uint32_t n_q_base;                            // entries contact tracing put into tomorrow's queue before the sweep
     uint32_t drained;                             // tomorrow's queue was already drained by k_resolve (detections parked in drain_det)
     int32_t ct_cases;
     int32_t vacc_cursor[RB_MAX_VACC];
     // ---- atomics of the grid kernels, one line per group
+    alignas(128) uint32_t n_list[2];              // entries of the two active lists
     alignas(128) uint32_t n_items;
     alignas(128) uint32_t n_succ;
     alignas(128) int32_t exposed_per_day;
@@ -126,14 +135,16 @@ struct RepCtr {
 };
 
 struct Eng {
-    int32_t dbg;                                   // measurement aid: 1/2/3 skip a sweep stage (timing experiments only)
+    int32_t dbg;                                   // measurement aid: 9 = the day-boundary kernels record cycles per phase (RepCtr::dbg_t)
     int32_t N, Npad, n_ages, n_groups, n_variants, R, max_days, row_len, n_import_classes, fhalf;
     uint32_t cap_items, cap_succ, cap_events, cap_queue;
     uint32_t *hot;
     AgentRec *rec;
     uint32_t *sus;                                 // [R][sus_words] 1 bit per agent: still SUSCEPTIBLE (L2-resident gather target)
     int32_t sus_words;
-    uint32_t *act;                                 // [R][sus_words] 1 bit per agent: has work in today's sweep (infected, or removed and not yet counted)
+    uint32_t *det;                                 // [R][sus_words] 1 bit per agent: detected by a test-queue drain (the sweep consults it once contact tracing has been on)
+    uint2 *alist;                                  // [R][2][cap_list] active lists: (agent, copy of its packed word with CURRENT day counters)
+    uint32_t cap_list;
     uint2 *items;
     Attempt *succ;
     unsigned long long *ev_key; int32_t *ev_agent;
@@ -209,6 +220,11 @@ __device__ __forceinline__ uint32_t sweep_pos(const Eng &G, const RepCtr *c, uin
     uint32_t s = feistel(a, (uint32_t)G.N, G.fhalf, c->fkey[0], c->fkey[1], c->fkey[2], c->fkey[3]);
     return s >= c->start ? s - c->start : s + (uint32_t)G.N - c->start;
 }
+// A test-queue drain detected agent a (person_detect, main.pyx:294-298).  The sweep keeps its own copies of the active
+// agents' words; detections it cannot foresee (contact tracing) reach it through this bitmap.
+__device__ __forceinline__ void mark_detected(const Eng &G, int r, int32_t a) {
+    atomicOr(&G.det[(size_t)r * G.sus_words + (a >> 5)], 1u << (a & 31));
+}
 __device__ __forceinline__ void count_add(RepCtr *c, int attr, int age, int d) { atomicAdd(&c->counts[attr][age], d); }
 __device__ __forceinline__ void set_problem(RepCtr *c, int p) { atomicCAS(&c->problem, 0, p); }
 
@@ -233,8 +249,9 @@ __device__ __forceinline__ int symptom_severity(const rb_variant *v, int age, fl
 
 // person_infect, main.pyx:209-235 + Population.infect :1576-1582.  `src_h` = packed word of the infector
 // (ignored when src < 0).  Severity and incubation use wild-type parameters (variant_idx is still 0 there).
+// `list`: the active list the new entry goes to (0 / 1), or -1 for none (the caller rebuilds the lists afterwards).
 __device__ void device_infect(const Eng &G, int r, RepCtr *c, int32_t t, int32_t src, uint32_t src_h, int variant,
-                              int slot, bool fresh) {
+                              int slot, bool fresh, int list, bool has_list) {
     const size_t base = (size_t)r * G.Npad;
     const int day = c->day;
     // the two atomics whose results are needed go first; the draws below hide their round trip
@@ -263,10 +280,18 @@ __device__ void device_infect(const Eng &G, int r, RepCtr *c, int32_t t, int32_t
     // a SUSCEPTIBLE agent's word carries nothing but the vaccinated flag, which vacc_day implies
     uint32_t nh = (vd >= 0 ? H_VACC : 0u) | RB_INCUBATION | ((uint32_t)sev << 3) | ((uint32_t)variant << 8) | ((uint32_t)dl << 14);
     if (fresh) nh |= H_FRESH;
-    if (c->testing_mode == RB_ALL_WITH_SYMPTOMS_CT) nh |= H_LIST;
+    if (has_list) nh |= H_LIST;      // person_infect, main.pyx:227-233: an infectee list only under contact tracing
     G.hot[base + t] = nh;
     atomicAnd(&G.sus[(size_t)r * G.sus_words + (t >> 5)], ~(1u << (t & 31)));
-    atomicOr(&G.act[(size_t)r * G.sus_words + (t >> 5)], 1u << (t & 31));
+    if (list >= 0 && owns(G, (uint32_t)t)) {      // from now on the sweep visits this agent: one warp-aggregated append
+        const unsigned am = __activemask();
+        const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
+        uint32_t b = 0;
+        if (lane == leader) b = atomicAdd(&c->n_list[list], (uint32_t)__popc(am));
+        b = __shfl_sync(am, b, leader) + __popc(am & ((1u << lane) - 1u));
+        if (b < G.cap_list) G.alist[((size_t)r * 2 + list) * G.cap_list + b] = make_uint2((uint32_t)t, nh);
+        else set_problem(c, RB_OTHER_FAILURE);
+    }
     count_add(c, RB_A_SUSCEPTIBLE, age, -1);
     count_add(c, RB_A_INFECTED, age, 1);
     count_add(c, RB_A_ALL_INFECTED, age, 1);

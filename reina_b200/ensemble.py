@@ -2,12 +2,15 @@
 
 The workload shards as independent units: every rank (one process per GPU) advances its own replicas
 (`Context(n_replicas=R, random_seed=seed0 + rank * R)`) with no data-path collective; the only exchange is the
-final reduce of the daily curves -- sum and sum of squares per (day, series) -- over `torch.distributed`
-(NCCL on GPUs, gloo in the CPU tests).  Replaces the reference's broken `run_monte_carlo` process pool
-(calc/simulation.py:349-385).  torch is plumbing only (process group + all_reduce); without an initialised
-process group everything here is plain numpy.
+final reduce of the daily curves -- sum and sum of squares per (day, series).  On GPUs that reduce is ONE ncclAllReduce
+on device buffers through the engine's own C-ABI (`Context.moments(reduce=True)` -> rb_reduce_moments); percentile
+bands gather the members' rows over the same communicator.  Replaces the reference's broken `run_monte_carlo` process
+pool (calc/simulation.py:349-385).  No framework is imported here: a communicator is any object with rank / size /
+allreduce / allgather / barrier (reina_b200/comm.py; the CPU tests pass an adapter over a gloo group).
 """
 import numpy as np
+
+from .comm import LocalComm
 
 
 def curve_moments(rows):
@@ -16,25 +19,12 @@ def curve_moments(rows):
     return x.sum(axis=0), (x * x).sum(axis=0), x.shape[0]
 
 
-def _dist():
-    try:
-        import torch.distributed as dist
-    except Exception:
-        return None
-    return dist if dist.is_available() and dist.is_initialized() else None
-
-
-def reduce_moments(s1, s2, n):
-    """All-reduce (sum) of the curve moments over the process group, if there is one."""
-    dist = _dist()
-    if dist is None or dist.get_world_size() == 1:
+def reduce_moments(s1, s2, n, comm=None):
+    """All-reduce (sum) of host-side curve moments over the communicator, if there is one."""
+    comm = comm or LocalComm()
+    if comm.size == 1:
         return s1, s2, n
-    import torch
-    t = torch.from_numpy(np.concatenate([s1.ravel(), s2.ravel(), [float(n)]]))
-    if dist.get_backend() == 'nccl':
-        t = t.cuda()
-    dist.all_reduce(t)
-    t = t.cpu().numpy()
+    t = comm.allreduce(np.concatenate([np.ravel(s1), np.ravel(s2), [float(n)]]), 'sum')
     k = s1.size
     return t[:k].reshape(s1.shape), t[k:2 * k].reshape(s2.shape), int(round(t[-1]))
 
@@ -53,19 +43,14 @@ def percentile_bands(rows, q=(5, 25, 50, 75, 95)):
     return {int(k): p[i] for i, k in enumerate(q)}
 
 
-def gather_rows(rows):
-    """All ranks' stats rows on every rank (percentiles need the members, not just the moments): all_gather over the
-    process group, identity without one."""
-    dist = _dist()
-    if dist is None or dist.get_world_size() == 1:
-        return np.asarray(rows)
-    import torch
-    t = torch.from_numpy(np.ascontiguousarray(rows))
-    if dist.get_backend() == 'nccl':
-        t = t.cuda()
-    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
-    dist.all_gather(out, t)
-    return np.concatenate([o.cpu().numpy() for o in out], axis=0)
+def gather_rows(rows, comm=None):
+    """All ranks' stats rows on every rank (percentiles need the members, not just the moments)."""
+    comm = comm or LocalComm()
+    rows = np.ascontiguousarray(rows)
+    if comm.size == 1:
+        return rows
+    out = comm.allgather(rows)                       # [rank, replica, day, series]
+    return out.reshape((-1,) + rows.shape[1:])
 
 
 def seeds_for_rank(seed0, replicas_per_rank, rank):
@@ -73,12 +58,21 @@ def seeds_for_rank(seed0, replicas_per_rank, rank):
     return seed0 + rank * replicas_per_rank
 
 
-def run_ensemble(make_context, days, replicas_per_rank, seed0=0, rank=0):
+def run_ensemble(make_context, days, replicas_per_rank, seed0=0, comm=None):
     """Run this rank's share and return the GLOBAL ensemble mean / std of every raw stats column.
 
-    make_context(n_replicas, random_seed) -> reina_b200.model.Context with interventions added."""
+    make_context(n_replicas, random_seed) -> reina_b200.model.Context with interventions added.  `comm` None: the
+    engine's own NCCL communicator is joined from the launcher's environment (reina_b200.comm.connect) and the reduce
+    runs on the device; any other communicator object reduces the host-side moments."""
+    from . import comm as _comm
+    rank = comm.rank if comm is not None else _comm.world()[0]
     ctx = make_context(replicas_per_rank, seeds_for_rank(seed0, replicas_per_rank, rank))
+    if comm is None:
+        comm = _comm.connect(ctx._engine)
     ctx.run(days)
-    s1, s2, n = reduce_moments(*ctx.moments(0, days))      # reduced over replicas on the device, over ranks by NCCL/gloo
+    if isinstance(comm, _comm.EngineComm) and comm.engine is ctx._engine:
+        s1, s2, n = ctx.moments(0, days, reduce=True)        # device-side: k_moments + one ncclAllReduce
+    else:
+        s1, s2, n = reduce_moments(*ctx.moments(0, days), comm=comm)
     mean, std = mean_std(s1, s2, n)
-    return dict(mean=mean, std=std, n=n, names=ctx.row_layout())
+    return dict(mean=mean, std=std, n=n, names=ctx.row_layout(), context=ctx, comm=comm)

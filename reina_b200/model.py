@@ -308,6 +308,7 @@ class Context:
         self.start_date = start_date
         self.day = 0
         self.interventions = []
+        self._direct = []       # apply_intervention() calls made directly by the caller, with the day they were made on
         self._contacts_per_day = ContactMatrix._records(population_params['contacts_per_day'])
         self._n_variants = len(variants)
         self._reset_host_state()
@@ -316,6 +317,8 @@ class Context:
     def _reset_host_state(self):
         """Host half of a fresh Context: HealthcareSystem / Population settings and the contact matrix."""
         self.contact_matrix = ContactMatrix(self._contacts_per_day, self.n_ages)
+        for entry in self._direct:
+            entry[2] = False
         # HealthcareSystem host-side settings (main.pyx:461-471)
         self._testing_mode = NO_TESTING
         self._p_detected_anyway = f32(0)
@@ -340,13 +343,17 @@ class Context:
         return (d + timedelta(days=self.day)).isoformat()
 
     def add_intervention(self, iv):                    # main.pyx:1810-1811
+        self._replan_from_today()
+        self.interventions.append(iv)
+
+    def _replan_from_today(self):
+        """Days beyond today may have been planned ahead (after reset() / load_state(), the schedule is kept because it
+        does not depend on the seed): drop them, so that a change made now takes effect from today's iterate() on."""
         if len(self._plan) > self.day:
-            # days beyond today were planned ahead (after reset()): re-plan them with the new list
             done = self.day
             self._reset_host_state()
             for _ in range(done):
                 self._plan_next_day()
-        self.interventions.append(iv)
 
     def find_variant(self, variant_str):               # main.pyx:1868-1878
         if variant_str is None:
@@ -357,6 +364,13 @@ class Context:
         raise Exception('Variant %s not found' % variant_str)
 
     def apply_intervention(self, iv):                  # main.pyx:1880-1960
+        """Part of the reference surface (calc/simulation.py:321 calls it directly): takes effect immediately, i.e. from
+        the next iterate() on.  The host keeps it with the day it was made on, so that re-planning replays it."""
+        self._replan_from_today()
+        self._apply(iv)                                # raises for an unknown type, like the reference
+        self._direct.append([self.day, iv, True])      # [day, intervention, applied to the current host state]
+
+    def _apply(self, iv):
         params = iv.get_param_values()
         t = iv.type
         if t == 'test-all-with-symptoms':
@@ -370,7 +384,10 @@ class Context:
         elif t == 'build-new-hospital-beds':
             self._pending['beds'] += params['beds']
         elif t == 'import-infections':
-            self._pending['imports'].append((int(params['amount']), self.find_variant(params.get('variant'))))
+            # infects immediately in the reference (main.pyx:1897-1899): the new cases get an infectee list iff contact
+            # tracing is the testing mode at THIS point of the day's intervention list (person_infect, :227-233)
+            self._pending['imports'].append((int(params['amount']), self.find_variant(params.get('variant')),
+                                             self._testing_mode == ALL_WITH_SYMPTOMS_CT))
         elif t == 'import-infections-weekly':
             shares = [0] * len(self.variant_names)
             for pn in params.keys():
@@ -448,9 +465,12 @@ class Context:
         self._engine.sync()
         return self._engine.read_stats(day0, days)
 
-    def moments(self, day0=0, days=None):
-        """Ensemble moments reduced on the device: (sum, sum of squares, n_replicas) of every stats column per day."""
+    def moments(self, day0=0, days=None, reduce=False):
+        """Ensemble moments reduced on the device: (sum, sum of squares, n_replicas) of every stats column per day.
+        reduce=True sums them over the ranks of the engine's NCCL communicator as well (rb_reduce_moments)."""
         days = self.day - day0 if days is None else days
+        if reduce:
+            return self._engine.reduce_moments(day0, days)
         s1, s2 = self._engine.read_moments(day0, days)
         return s1, s2, self.n_replicas
 
@@ -464,7 +484,11 @@ class Context:
 
     def reset(self, random_seed):
         """A fresh Context(random_seed=...) with the same inputs and interventions, without reallocating
-        device memory.  The planned schedule is kept (it does not depend on the seed)."""
+        device memory.  The planned schedule is kept (it does not depend on the seed); interventions applied directly
+        with apply_intervention() belong to the old run and are dropped."""
+        if self._direct:
+            self._direct = []
+            self._reset_host_state()
         self._engine.reset(random_seed)
         self.day = 0
         self._state_day = -1
@@ -514,10 +538,15 @@ class Context:
     def _plan_next_day(self):
         """Host half of one iterate(): interventions dated that day (main.pyx:2012-2015), then the settings
         Population.init_day (:1687-1699) and HealthcareSystem.iterate (:547-558) read.  Appends to the plan."""
-        today = (date.fromisoformat(self.start_date) + timedelta(days=len(self._plan))).isoformat()
+        index = len(self._plan)
+        today = (date.fromisoformat(self.start_date) + timedelta(days=index)).isoformat()
+        for entry in self._direct:                     # re-planning: direct apply_intervention() calls made before that day's iterate()
+            if entry[0] == index and not entry[2]:
+                self._apply(entry[1])
+                entry[2] = True
         for iv in self.interventions:
             if iv.date == today:
-                self.apply_intervention(iv)
+                self._apply(iv)
         dp = DayParams()
         dp.testing_mode = self._testing_mode
         dp.p_detected_anyway = self._p_detected_anyway
@@ -527,8 +556,10 @@ class Context:
         if len(imports) > _abi.RB_MAX_IMPORT_EVENTS:
             raise ValueError('more than %d import events on one day' % _abi.RB_MAX_IMPORT_EVENTS)
         dp.n_imports = len(imports)
-        for i, (amount, variant) in enumerate(imports):
+        dp.import_traced = 0
+        for i, (amount, variant, traced) in enumerate(imports):
             dp.import_amount[i], dp.import_variant[i] = amount, variant
+            dp.import_traced |= int(bool(traced)) << i
         self._pending = dict(beds=0, icu=0, imports=[])
         # ContactMatrix.init_day, main.pyx:1285-1288
         cm = self.contact_matrix

@@ -31,9 +31,13 @@ def _context_key(variables, scenario):
 
 
 class SimulationWorker:
-    def __init__(self, device=0, max_contexts=4, callback_day_interval=30, context_factory=None):
+    def __init__(self, device=0, max_contexts=4, callback_day_interval=30, context_factory=None, max_finished_jobs=256):
         self.device = device
         self.max_contexts = max_contexts
+        # finished jobs are kept for polling clients, the oldest are dropped beyond this many (the reference's cache
+        # entries expire, simulation_thread.py:40-60); release(job) drops one at once
+        self.max_finished_jobs = max_finished_jobs
+        self._finished = []
         self.callback_day_interval = callback_day_interval
         # injectable so that the host logic can be tested without a GPU (tests pass the CPU oracle's library)
         self._factory = context_factory or (lambda v, scenario: simulation.make_context(v, device=self.device, scenario=scenario))
@@ -66,8 +70,17 @@ class SimulationWorker:
             self._jobs[job]['cancelled'] = True
 
     def wait(self, job, timeout=None):
-        self._jobs[job]['done'].wait(timeout)
+        with self._lock:
+            done = self._jobs[job]['done']
+        done.wait(timeout)
         return self.results(job)
+
+    def release(self, job):
+        """Forget a job and its DataFrames (a finished one, or one whose results nobody will ask for)."""
+        with self._lock:
+            self._jobs.pop(job, None)
+            if job in self._finished:
+                self._finished.remove(job)
 
     def close(self):
         self._queue.put(None)
@@ -96,7 +109,10 @@ class SimulationWorker:
             if item is None:
                 return
             job, v, scenario = item
-            j = self._jobs[job]
+            with self._lock:
+                j = self._jobs.get(job)
+            if j is None:                   # released before it started
+                continue
             try:
                 ctx, reused = self._context_for(v, scenario)
                 j['reused_context'] = reused
@@ -118,4 +134,8 @@ class SimulationWorker:
                     j['error'] = str(e) or type(e).__name__
             with self._lock:
                 j['finished'] = True
+                if job in self._jobs:
+                    self._finished.append(job)
+                while len(self._finished) > self.max_finished_jobs:
+                    self._jobs.pop(self._finished.pop(0), None)
             j['done'].set()

@@ -1,12 +1,14 @@
 """Population-sharded runs (BASELINE configs[4]): one process per GPU, every rank builds the same Context and joins
-the others through `shard=(rank, nranks, unique_id)`; the engine exchanges the day's cross-shard events with one NCCL
-all-gather per simulated day (include/reina_b200.h, rb_shard_init).
+the others through `shard=(rank, nranks, unique_id)`; the engine exchanges the day's cross-shard events over NVLink peer
+memory (include/reina_b200.h, rb_shard_init).
 
-`torch.distributed` is used only to hand rank 0's NCCL unique id to the other ranks (any backend, gloo works on CPU).
+Rank 0's NCCL unique id reaches the other ranks of the node through a file (reina_b200/comm.py); a caller that already
+has a process group of its own (`dist`: anything with is_initialized / get_rank / get_world_size / broadcast_object_list)
+can hand it over through that instead.
 """
 import os
 
-from . import _abi
+from . import _abi, comm
 
 
 def world():
@@ -20,7 +22,15 @@ def exchange_unique_id(make_id=None, dist=None):
     torch.distributed module (or None for a single process); `make_id` defaults to the CUDA library's
     rb_shard_unique_id and is injectable so that the plumbing can be tested on CPU."""
     make_id = make_id or _abi.shard_unique_id
-    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+    if dist is None or not dist.is_initialized():
+        rank, n, _ = world()
+        if n == 1:
+            return make_id()
+        uid = comm.broadcast_bytes(make_id() if rank == 0 else None, rank, key='shard')
+        if len(uid) != 128:
+            raise _abi.EngineError('unique id hand-off failed')
+        return uid
+    if dist.get_world_size() == 1:
         return make_id()
     box = [make_id() if dist.get_rank() == 0 else None]
     dist.broadcast_object_list(box, src=0)
@@ -35,7 +45,7 @@ def shard_spec(dist=None, exchange_capacity=0.0, make_id=None):
     if dist is not None and dist.is_initialized():
         rank, n = dist.get_rank(), dist.get_world_size()
     else:
-        rank, n = 0, 1
+        rank, n, _ = world()
     return (rank, n, exchange_unique_id(make_id, dist), exchange_capacity)
 
 

@@ -148,3 +148,28 @@ def diff_report(gpu, cpu, days):
         if not np.array_equal(gpu._engine.read_available(r), cpu._engine.read_available(r)):
             out.append('replica %d free beds/icu differ' % r)
     return out
+
+
+class TorchComm:
+    """Adapter that gives a torch.distributed process group (gloo in the CPU tests) the communicator interface of
+    reina_b200/comm.py: rank, size, allreduce(x, op), allgather(x), barrier()."""
+
+    def __init__(self, dist):
+        self.dist = dist
+        self.rank, self.size = dist.get_rank(), dist.get_world_size()
+
+    def allreduce(self, x, op='sum'):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).copy())
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM if op == 'sum' else self.dist.ReduceOp.MAX)
+        return t.numpy()
+
+    def allgather(self, x):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(x).copy())
+        out = [torch.empty_like(t) for _ in range(self.size)]
+        self.dist.all_gather(out, t)
+        return np.stack([o.numpy() for o in out])
+
+    def barrier(self):
+        self.dist.barrier()

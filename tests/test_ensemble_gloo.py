@@ -30,11 +30,11 @@ def _worker(rank, world, port, out_dir):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    res = ensemble.run_ensemble(_make, days=50, replicas_per_rank=2, seed0=300, rank=rank)
+    comm = helpers.TorchComm(dist)
+    res = ensemble.run_ensemble(_make, days=50, replicas_per_rank=2, seed0=300, comm=comm)
     # percentile bands need the members, not just the moments: all ranks' rows are gathered over the process group
-    ctx = _make(2, ensemble.seeds_for_rank(300, 2, rank))
-    ctx.run(50)
-    rows = ensemble.gather_rows(ctx.series(0, 50))
+    ctx = res['context']
+    rows = ensemble.gather_rows(ctx.series(0, 50), comm)
     bands = ensemble.percentile_bands(rows, (0, 50, 100))
     np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), mean=res['mean'], std=res['std'], n=res['n'],
              n_rows=rows.shape[0], lo=bands[0], median=bands[50], hi=bands[100])

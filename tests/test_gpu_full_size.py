@@ -94,3 +94,101 @@ def test_simulate_individuals_frames(cuda_lib):
     assert df.shape[0] == 120 and adf.shape == (120, 12 * 9)
     assert df['susceptible'].iloc[0] == 479861 and df['all_infected'].iloc[-1] > 1000
     assert str(df.index[0].date()) == '2020-02-18'
+
+
+# ---------------------------------------------------------------------------------------------------
+# bit-exact at the FULL size and in the launch geometry bench.py times
+# ---------------------------------------------------------------------------------------------------
+N_HUS = 1685983
+
+
+def test_full_size_single_seed_bit_exact(cuda_lib, oracle_lib):
+    """BASELINE configs[1] literally: HUS, 1,685,983 agents x 180 days, one seed -- CUDA == sequential oracle in every
+    stats row, every agent field, the test queue and the capacity counters (full-size bucket counts, list capacities
+    and age-block walks; the single-seed launch geometry)."""
+    kw = dict(seed=31337, max_days=181)
+    gpu = helpers.make_context(cuda_lib, **kw)
+    cpu = helpers.make_context(oracle_lib, **kw)
+    assert gpu.n_agents == N_HUS
+    gpu.run(180)
+    cpu.run(180)
+    rep = helpers.diff_report(gpu, cpu, 180)
+    assert not rep, '\n'.join(rep)
+    gpu.close()
+
+
+def test_bench_geometry_bit_exact(cuda_lib, oracle_lib):
+    """The exact configuration `python bench.py` times -- 256 HUS replicas, the engine's DEFAULT replica groups / grids /
+    streams for that count -- is bit-identical, for replicas 0, 100 and 255, to three single-seed CUDA runs AND to the
+    sequential oracle (stats rows + every agent field)."""
+    R, seed0 = 256, 900000
+    ens = helpers.make_context(cuda_lib, seed=seed0, n_replicas=R, max_days=181)
+    assert ens.n_agents == N_HUS
+    for k in ('RB_GROUPS', 'RB_GROUP_WAVE_PCT', 'RB_WIDE_CTAS', 'RB_WIDE_MIN'):
+        assert k not in os.environ, 'this test must run with the default launch geometry'
+    ens.run(180)
+    rows = ens.series(0, 180)
+    one = helpers.make_context(cuda_lib, seed=seed0, max_days=181)
+    for r in (0, 100, 255):
+        cpu = helpers.make_context(oracle_lib, seed=seed0 + r, max_days=181)
+        cpu.run(180)
+        ref = cpu.series(0, 180)[0]
+        bad = np.argwhere(rows[r] != ref)
+        assert len(bad) == 0, 'replica %d of the ensemble differs from the oracle first at (day, col) %s' % (r, bad[0])
+        ca = cpu._engine.read_agents(0)
+        assert np.array_equal(ens._engine.read_agents(r), ca), 'replica %d: agent fields differ from the oracle' % r
+        assert np.array_equal(np.sort(ens._engine.read_queue(r)), np.sort(cpu._engine.read_queue(0)))
+        assert np.array_equal(ens._engine.read_available(r), cpu._engine.read_available(0))
+        one.reset(seed0 + r)
+        one.run(180)
+        assert np.array_equal(one.series(0, 180)[0], rows[r]), 'replica %d differs from the single-seed CUDA run' % r
+        assert np.array_equal(one._engine.read_agents(0), ca)
+    ens.close()
+    one.close()
+
+
+def test_monte_carlo_driver_on_cuda(cuda_lib, oracle_lib, tmp_path):
+    """simulation.run_monte_carlo on the GPU: 128 seeds at 64 per launch; two sampled runs equal the
+    oracle's single-seed runs row for row; percentile bands bracket the median."""
+    from reina_b200 import inputs, simulation
+    v = inputs.default_variables(simulation_days=90, area_name='Varsinais-Suomi')
+    df, bands = simulation.run_monte_carlo('default', n_seeds=128, seed0=5000, variables=v, replicas_per_launch=64,
+                                           csv_path=str(tmp_path / 'mc.csv'), bands=(5, 50, 95))
+    assert sorted(df['run'].unique()) == list(range(5000, 5128)) and len(df) == 128 * 90
+    assert os.path.getsize(tmp_path / 'mc.csv') > 0
+    assert (bands[5] <= bands[50]).all().all() and (bands[50] <= bands[95]).all().all()
+    for run in (5003, 5100):                          # one from each launch
+        cpu = simulation.make_context(v, _library=oracle_lib)
+        cpu.reset(run)
+        d2, _ = simulation.simulate_individuals(v, context=cpu)
+        mine = df[df['run'] == run]
+        for col in ('infected', 'all_infected', 'dead', 'exposed_per_day', 'exposures_work', 'available_hospital_beds', 'r'):
+            assert np.array_equal(mine[col].to_numpy(dtype=float), d2[col].to_numpy(dtype=float)), (run, col)
+
+
+def test_simulation_worker_on_cuda(cuda_lib, oracle_lib):
+    """serving.SimulationWorker over real CUDA contexts: two seeds through one resident context
+    (allocated once, reset in place), results equal the oracle's, and a cancelled job stops."""
+    from reina_b200 import inputs, serving, simulation
+    w = serving.SimulationWorker(device=0, callback_day_interval=20)
+    try:
+        jobs = []
+        for seed in (11, 12):
+            v = inputs.default_variables(simulation_days=60, area_name='Varsinais-Suomi', random_seed=seed)
+            jobs.append((seed, v, w.submit(v)))
+        for seed, v, job in jobs:
+            res = w.wait(job, timeout=300)
+            assert res['finished'] and res['error'] is None, res['error']
+            cpu = simulation.make_context(v, _library=oracle_lib)
+            d2, a2 = simulation.simulate_individuals(v, context=cpu)
+            cols = [c for c in d2.columns if c != 'us_per_infected']
+            assert np.array_equal(res['total'][cols].to_numpy(dtype=float), d2[cols].to_numpy(dtype=float)), seed
+            assert np.array_equal(res['age_groups'].to_numpy(), a2.to_numpy())
+        assert w.results(jobs[0][2])['reused_context'] is False and w.results(jobs[1][2])['reused_context'] is True
+        v = inputs.default_variables(simulation_days=60, area_name='Varsinais-Suomi', random_seed=13)
+        job = w.submit(v)
+        w.cancel(job)
+        res = w.wait(job, timeout=300)
+        assert res['finished'] and res['error'] == 'cancelled'
+    finally:
+        w.close()

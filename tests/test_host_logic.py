@@ -305,3 +305,97 @@ def test_surface_equals_the_reference_module(oracle_lib):
             ctx.get_population_stats('nonsense')
         with pytest.raises(Exception):
             ctx.apply_intervention(inputs.Intervention('no-such-intervention', '2020-01-01'))
+
+
+# ---------------------------------------------------------------------------------------------------
+# round-2 host logic: intervention ordering, direct apply_intervention, input validation, job pruning
+# ---------------------------------------------------------------------------------------------------
+def test_import_sees_the_testing_mode_of_its_turn(oracle_lib):
+    """Interventions of one date are applied in list order (main.pyx:2012-2015) and import-infections infects at once
+    (:1897-1899): the imported cases get an infectee list iff contact tracing was the mode when the import's turn came
+    (person_infect, :227-233), not the mode the day ends with."""
+    counts = helpers.small_population(6000)
+    day = '2020-02-20'
+
+    def run(order):
+        ivs = [inputs.iv_tuple_to_obj(t) for t in order]
+        ctx = helpers.make_context(oracle_lib, age_count_override=counts, seed=4, interventions=ivs, max_days=8)
+        ctx.run(3)
+        return ctx._plan[2], ctx._engine.read_agents(0)
+
+    imp, ct, plain = ['import-infections', day, 30], ['test-with-contact-tracing', day, 50], ['test-all-with-symptoms', day]
+    dp, ag = run([imp, ct])                      # imported BEFORE tracing starts: no lists, although the day ends in CT mode
+    assert dp.import_traced == 0 and dp.testing_mode == model.ALL_WITH_SYMPTOMS_CT
+    assert ((ag['state'] > 0).sum() >= 25) and not (ag['flags'][ag['state'] > 0] & 8).any()
+    dp, ag = run([ct, imp])                      # tracing first: every imported case owns a list
+    assert dp.import_traced == 1
+    assert (ag['flags'][ag['state'] > 0] & 8).all()
+    dp, ag = run([ct, imp, plain, ['import-infections', day, 10]])      # CT only for the first of two imports
+    assert dp.import_traced == 0b01 and dp.n_imports == 2 and dp.testing_mode == model.ALL_WITH_SYMPTOMS
+    n_list = int((ag['flags'][ag['state'] > 0] & 8).astype(bool).sum())
+    assert 25 <= n_list <= 30 and (ag['state'] > 0).sum() >= n_list + 8
+
+
+def test_direct_apply_intervention_takes_effect_from_today(oracle_lib):
+    """apply_intervention is reference surface (calc/simulation.py:321) and acts immediately.  After reset() the plan
+    already extends past today: a direct call must re-plan from today instead of being ignored, and a later
+    add_intervention must not lose it."""
+    counts = helpers.small_population(8000)
+    imp = inputs.iv_tuple_to_obj(['import-infections', '2020-01-01', 40])        # its date is irrelevant for a direct call
+
+    def infected_after(ctx, days):
+        ctx.run(days)
+        G = len(ctx.age_group_labels)
+        return int(ctx.series(0, ctx.day)[0, -1, 3 * G:4 * G].sum())
+
+    base = helpers.make_context(oracle_lib, age_count_override=counts, seed=6, interventions=[], max_days=40)
+    assert infected_after(base, 12) == 0
+    base.reset(6)                                    # plan of 12 days kept
+    assert len(base._plan) == 12 and base.day == 0
+    base.run(5)
+    base.apply_intervention(imp)                     # day 5: must not be swallowed by the 7 days planned ahead
+    assert len(base._plan) == 5
+    got = infected_after(base, 6)
+    assert got >= 35, got
+    assert base._plan[5].n_imports == 1 and base._plan[5].import_amount[0] == 40
+    base.add_intervention(inputs.iv_tuple_to_obj(['limit-mobility', '2020-03-01', 30]))     # re-plans; the direct call survives
+    base.run(1)
+    assert base._plan[5].n_imports == 1 and len(base._plan) == 12
+    base.reset(9)                                    # a fresh run: the direct call belonged to the old one
+    assert infected_after(base, 12) == 0
+    with pytest.raises(Exception):
+        base.apply_intervention(inputs.Intervention('no-such-intervention', '2020-01-01'))
+
+
+def test_empty_contact_band_and_import_class_are_refused(oracle_lib):
+    """A contact row / import class that can be drawn but holds nobody would take `x % 0` for the person index: both
+    libraries refuse the input with an error instead (the reference would die with SIGFPE)."""
+    counts = helpers.small_population(4000)
+    counts[70:] = 0                                   # the whole 70+ band empty (every age has a row into it)
+    counts[30] += 4000 - counts.sum()
+    with pytest.raises(_abi.EngineError, match='empty'):
+        helpers.make_context(oracle_lib, age_count_override=counts)
+    counts = helpers.small_population(4000)
+    counts[:20] = 0                                   # import class 0-19 (weight 15 %) empty; contact bands 0-4 ... 15-19 too
+    counts[40] += 4000 - counts.sum()
+    with pytest.raises(_abi.EngineError, match='empty'):
+        helpers.make_context(oracle_lib, age_count_override=counts)
+
+
+def test_serving_worker_forgets_old_jobs(oracle_lib):
+    from reina_b200 import serving
+
+    def factory(v, scenario):
+        return helpers.make_context(oracle_lib, variables=v, scenario=scenario, seed=v['random_seed'],
+                                    age_count_override=helpers.small_population(3000), max_days=v['simulation_days'] + 1)
+    w = serving.SimulationWorker(context_factory=factory, callback_day_interval=5, max_finished_jobs=2)
+    v = inputs.default_variables(simulation_days=6)
+    jobs = [w.submit(dict(v, random_seed=s)) for s in range(4)]
+    for j in jobs[2:]:
+        assert w.wait(j, timeout=120)['finished']
+    assert set(w._jobs) == set(jobs[2:])              # the two oldest finished jobs were dropped
+    w.release(jobs[3])
+    assert set(w._jobs) == {jobs[2]}
+    with pytest.raises(KeyError):
+        w.results(jobs[0])
+    w.close()

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 for flag in (0, 1, 2, 3):
-    ctx = bench.make_context(R, 0, 180, seed=1)
+    ctx = bench.make_context(bench.workload_spec('hus'), R, 0, 180, seed=1)
     ctx.run(85)
     while len(ctx._plan) < 180: ctx._plan_next_day()
     ctx._engine.set_schedule(0, ctx._plan[:180])

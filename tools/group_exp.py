@@ -25,7 +25,7 @@ for cfg in a.configs.split(','):
         os.environ['RB_L2_FETCH'] = cfg.split(':')[2]
     os.environ['RB_GROUPS'] = ng
     os.environ['RB_GROUP_WAVE_PCT'] = pct
-    ctx = bench.make_context(a.replicas, 0, a.days, seed=1)
+    ctx = bench.make_context(bench.workload_spec('hus'), a.replicas, 0, a.days, seed=1)
     ms = []
     for step in range(2 + a.steps):
         ctx.reset(1000 + step)

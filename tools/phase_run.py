@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-ctx = bench.make_context(R, 0, 180, seed=1)
+ctx = bench.make_context(bench.workload_spec('hus'), R, 0, 180, seed=1)
 lib = ctx._engine.lib.dll
 lib.rb_debug_flag.argtypes = [ctypes.c_void_p, ctypes.c_int32]
 lib.rb_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
