@@ -631,7 +631,10 @@ __device__ void post_body(const Eng &G, const int r, SmemSmall &S, Team &T) {
     const int day = c->day;
     const int beds0 = c->avail_beds, icu0 = c->avail_icu;
     const uint32_t n_newq = c->n_newq;
+    const uint32_t old_l = c->lsel;
     if (G.dbg == 9 && T.tid == 0) c->dbg_last = clock64();
+    // the lists today's sweep has read are emptied: tomorrow's sweep writes them (nobody reads these counters before then)
+    for (uint32_t s = T.tid; s < G.n_seg; s += T.nth) *seg_count(G, r, old_l, s) = make_uint2(0u, 0u);
     if (n > 0) {
         BucketMap bm; bm.n_agents = (uint32_t)G.N; bm.n_prev = 0; bm.kind = 0;
         team_sort_pairs(T, ek, ea, n, G.cap_events, G.succ + (size_t)r * G.cap_succ, G.cap_succ, bm, sk, sv, S.warp_sums);
@@ -722,10 +725,7 @@ __device__ void post_body(const Eng &G, const int r, SmemSmall &S, Team &T) {
         c->qsel ^= 1u;
         c->n_queue = min(n_newq, G.cap_queue);
         c->n_newq = 0;
-        // the list today's sweep and k_resolve wrote becomes tomorrow's; the one just read is emptied for tomorrow's sweep
-        const uint32_t old = c->lsel;
-        c->lsel = old ^ 1u;
-        c->n_list[old] = 0u;
+        c->lsel = old_l ^ 1u;        // the lists today's sweep and k_resolve wrote become tomorrow's
         c->day = day + 1;            // main.pyx:2009
     }
 }

@@ -14,8 +14,11 @@
 #define EX_THREADS 128
 #endif
 #ifndef EX_CTAS_PER_SM
-#define EX_CTAS_PER_SM 12        // CTAs per SM the grid is sized for: all resident (40 registers), one wave
+#define EX_CTAS_PER_SM 24        // CTAs per SM the grid is sized for: two waves of the 12 resident ones.  A replica's CTAs share its
+                                 // work items by grid stride, so a finer grid evens out the tail: measured on the peak day 8 / 10 /
+                                 // 12 / 16 / 24 per SM: 553 / 519 / 588 (1.04 waves: the worst case) / 504 / 482 us
 #endif
+#define EX_RESIDENT_PER_SM 12    // 42 registers
 #define EX_WARPS (EX_THREADS / 32)
 #define EX_RCAP 256
 
@@ -60,14 +63,14 @@ __device__ __forceinline__ void expose_survivors(const Eng &G, int r, RepCtr *c,
     b = __shfl_sync(0xffffffffu, b, 0);
     if (!ok) return;
     const uint32_t idx = b + __popc(okm & ((1u << lane) - 1u));
-    const unsigned long long key = ((unsigned long long)sweep_pos(G, c, a) << 7) | slot;
+    const unsigned long long key = ((unsigned long long)sweep_pos(G, r, c, a) << 7) | slot;
     if (idx < cap_succ) {
         succ[idx].cand = t; succ[idx].parent = a; succ[idx].key = key;
         if (!G.xbuf) atomicMin(&G.rec[base + t].winner, key);     // sharded: k_merge does it over every rank's list
     } else set_problem(cd, RB_OTHER_FAILURE);
 }
 
-__global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
+__global__ void __launch_bounds__(EX_THREADS, EX_RESIDENT_PER_SM) k_expose(Eng G) {
     __shared__ int s_place[RB_N_PLACES];
     __shared__ uint32_t s_ri[EX_WARPS][EX_RCAP], s_rx[EX_WARPS][EX_RCAP];
     const int r = blockIdx.y + G.r0;
@@ -89,13 +92,17 @@ __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
     uint32_t head = 0, tail = 0;
     uint32_t places = 0;                 // this thread's per-place counters, 5 bits each, flushed every 7 iterations
     int since_flush = 0;
-    for (uint32_t i0 = blockIdx.x * blockDim.x + warp * 32; i0 < n; i0 += gridDim.x * blockDim.x) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint2 nxt = make_uint2(0u, 0u);
+    if (blockIdx.x * blockDim.x + warp * 32 + lane < n) nxt = __ldcs(&items[blockIdx.x * blockDim.x + warp * 32 + lane]);
+    for (uint32_t i0 = blockIdx.x * blockDim.x + warp * 32; i0 < n; i0 += stride) {
         const uint32_t i = i0 + lane;
         const bool valid = i < n;
+        const uint2 it = nxt;
+        if (i + stride < n) nxt = __ldcs(&items[i + stride]);       // the next step's work item: in flight while this one is processed
         uint32_t words[4] = {0, 0, 0, 0}, ncnt = 0, age = 0, grp = 0;
         int kq = 0;
         if (valid) {
-            const uint2 it = items[i];
             grp = it.y & 31u; ncnt = ((it.y >> 5) & 3u) + 1u; age = (it.y >> 7) & 127u;
             const rb_variant *v = &G.variants[(it.y >> 20) & 3u];
             float si = v->iot[(it.y >> 14) & 31u];
@@ -108,24 +115,27 @@ __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
         }
         const int nrows = tb->n_rows[age];
         const uint32_t *cum24 = tb->cum24[age];
-        const uint16_t *guide = tb->guide[age];
+        const uint32_t *guide = tb->guide[age];
+        // get_one_contact (main.pyx:1290-1304): u = (word >> 8) / 2^24, the row is the first one with u < cum_p (an integer
+        // compare against ceil(cum_p 2^24)).  ONE guide entry, fetched from u's top bits, answers for its whole cell unless
+        // the cell holds several row boundaries (see DevTable::guide); the four gathers of a thread are issued together.
+        uint32_t gd[4];
+#pragma unroll
+        for (uint32_t w = 0; w < 4; w++) gd[w] = w < ncnt ? __ldg(&guide[words[w] >> (32 - GUIDE_BITS)]) : 0u;
 #pragma unroll
         for (uint32_t w = 0; w < 4; w++) {
             bool pass = false;
             uint32_t row = 0;
             if (w < ncnt) {
                 const uint32_t word = words[w];
-                // get_one_contact (main.pyx:1290-1304): u = (word >> 8) / 2^24, the row is the first one with u < cum_p, as an
-                // integer compare against ceil(cum_p 2^24).  The guide answers from u's top bits alone for a cell that
-                // lies inside one row; a cell with one boundary costs one compare; the rest walk on from the cell's first row.
-                const uint32_t k24 = word >> 8;
-                const uint32_t g = __ldg(&guide[k24 >> (24 - GUIDE_BITS)]);
+                const uint32_t k24 = word >> 8, g = gd[w], delta = (g >> 10) & 15u;
                 row = g & 127u;
                 uint32_t place = (g >> 7) & 7u;
-                if (g >> 14) {
-                    if (!(k24 < __ldg(&cum24[row]))) {
-                        if ((g >> 14) == 1u) row += (g >> 10) & 15u;
-                        else { row++; while ((int)row < nrows - 1 && !(k24 < __ldg(&cum24[row]))) row++; }   // last row on overrun: the reference fails there (p ~ 1e-15)
+                if (delta) {
+                    if (delta < 15u) {
+                        if ((k24 & ((1u << (24 - GUIDE_BITS)) - 1u)) >= (g >> 17)) { row += delta; place = (g >> 14) & 7u; }
+                    } else {
+                        while ((int)row < nrows - 1 && !(k24 < __ldg(&cum24[row]))) row++;   // last row on overrun: the reference fails there (p ~ 1e-15)
                         place = tb->place[age][row];
                     }
                 }
@@ -161,21 +171,34 @@ __global__ void __launch_bounds__(EX_THREADS) k_expose(Eng G) {
 // main.pyx:514-545: every queued agent is detected).  The per-age detection counts are parked in drain_det and booked
 // by the boundary at the point where the reference drains, so every stats row is unchanged.
 template <bool DRAIN>
-__global__ void __launch_bounds__(256) k_resolve(Eng G) {
+__global__ void __launch_bounds__(256, 4) k_resolve(Eng G) {
     const int r = blockIdx.y + G.r0;
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
     const uint32_t n = min(c->n_succ, G.cap_succ);
     const Attempt *succ = G.succ + (size_t)r * G.cap_succ;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const Attempt at = succ[i];
-        const unsigned long long w = G.rec[base + at.cand].winner;
-        const uint32_t src_h = G.hot[base + at.parent];       // in flight together with the conflict slot
-        if (w != at.key) continue;                             // first infector in sweep order wins
-        // infected during today's sweep: first visited tomorrow, so the entry goes to the list today's sweep has written
-        device_infect(G, r, c, (int32_t)at.cand, (int32_t)at.parent, src_h, 0, (int)(at.key & 127ull), false, (int)(c->lsel ^ 1u),
-                      c->testing_mode == RB_ALL_WITH_SYMPTOMS_CT);
-        G.rec[base + at.cand].winner = KEY_IDLE;
+    // two attempts per thread and pass: their gathers (conflict slot of the target, packed word of the infector) are in
+    // flight together.  Two attempts on one target cannot both hold the winning key, so their order does not matter.
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const int list = (int)(c->lsel ^ 1u);      // infected during today's sweep: first visited tomorrow, so the entry goes to the lists today's sweep has written
+    const bool has_list = c->testing_mode == RB_ALL_WITH_SYMPTOMS_CT;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+        const uint32_t j = i + stride;
+        const bool two = j < n;
+        const Attempt a0 = succ[i];
+        Attempt a1 = a0;
+        if (two) a1 = succ[j];
+        const unsigned long long w0 = G.rec[base + a0.cand].winner;
+        const uint32_t h0 = G.hot[base + a0.parent];
+        unsigned long long w1 = KEY_IDLE; uint32_t h1 = 0;
+        if (two) { w1 = G.rec[base + a1.cand].winner; h1 = G.hot[base + a1.parent]; }
+#pragma unroll 1
+        for (int k = 0; k < 2; k++) {
+            const Attempt at = k ? a1 : a0;
+            if ((k && !two) || (k ? w1 : w0) != at.key) continue;      // first infector in sweep order wins
+            device_infect(G, r, c, (int32_t)at.cand, (int32_t)at.parent, k ? h1 : h0, 0, (int)(at.key & 127ull), false, list, has_list);
+            G.rec[base + at.cand].winner = KEY_IDLE;
+        }
     }
     // verdict for the day boundary that follows: enough capacity events or queued tests to be worth a team of CTAs
     if (blockIdx.x == 0 && threadIdx.x == 0)

@@ -50,7 +50,7 @@ struct rb_engine {
     int n_table_slots;
     rb_day_params *d_sched;
     double *d_moments;                  // [2][max_days + 1][row_len] + 1: ensemble moments (rb_read_moments / rb_reduce_moments)
-    DevTable *h_stage; int n_stage;     // pinned staging ring for contact-table uploads
+    void *h_stage; int n_stage;         // pinned staging ring for contact-table uploads (4 x TABLE_HOST_BYTES)
     cudaEvent_t ev_stage[4];
     std::vector<rb_day_params> h_sched;
     std::vector<int32_t> age_start, age_counts;
@@ -146,6 +146,19 @@ static int init_counters(rb_engine *e, uint32_t seed) {
 }
 
 static int setup_groups(rb_engine *e, int sms);
+static void group_config(int R, int *n_groups, int *wave_pct);
+
+// k_resolve is a chain of dependent scattered accesses per infection (two infections in flight per thread): it wants as
+// many threads in flight as a day can bring infections -- up to ~1 / 128 of the agents -- and is indifferent to how many
+// of its CTAs find nothing to do.  Measured on the peak day of 256 HUS replicas (us): 2 / 4 / 8 / 16 CTAs per SM in total
+// 341 / 350 / 322 / 294; 52 CTAs per replica (13312 in all) 260.
+static int resolve_grid(int n_agents, int sms, int pct, int replicas) {
+    long long b = ((long long)n_agents / 128 + 255) / 256;
+    long long cap = (long long)sms * 16 * pct / 100 / replicas; if (cap < 64) cap = 64;
+    if (const char *s = getenv("RB_RESOLVE_BLOCKS")) cap = b = atoi(s);      // measurement aid
+    if (b > cap) b = cap;
+    return b < 1 ? 1 : (int)b;
+}
 
 extern "C" void rb_destroy(rb_engine *e) {
     if (!e) return;
@@ -214,10 +227,25 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     G.cap_events = pow2_at_least((uint64_t)N / 16 + 2048);
     G.cap_queue = pow2_at_least((uint64_t)N / 8 + 2048);
     const size_t RN = (size_t)R * G.Npad;
-    G.cap_list = (uint32_t)G.Npad;                        // an agent is listed at most once
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
+    const int sms = prop.multiProcessorCount;
+    {   // Active-list segments (state.cuh, Eng::alist)
+        // two per warp of the sweep grid a replica gets in the production geometry (its replica group's share of a wave):
+        // a warp streams a segment from end to end, so segments are the unit of load balance -- but every segment costs a
+        // dependent round trip to memory before its first entry arrives, so there should not be many more than warps; and
+        // none so small that it holds fewer than ~256 agents
+        int ng, pct;
+        group_config(R, &ng, &pct);
+        long long ctas = (long long)sms * SW_CTAS_PER_SM * (ng > 1 ? pct : 100) / 100 / ((R + ng - 1) / ng);      // as setup_groups sizes the grid
+        if (ctas < 1) ctas = 1;
+        long long S = 2 * ctas * SW_WARPS, most = (long long)N / 256;
+        if (S > most) S = most;
+        G.n_seg = (uint32_t)(S < 1 ? 1 : S);
+        G.seg_cap = ((uint32_t)N + G.n_seg - 1) / G.n_seg;        // agents a with a % n_seg == s: never more than this
+    }
     G.sus_words = ((G.Npad + 31) / 32 + 32 + 3) & ~3;     // multiple of 4 words: the sweep reads the bitmaps 16 bytes at a time
-    if (dalloc(e, &G.hot, RN) || dalloc(e, &G.rec, RN) ||
-        dalloc(e, &G.sus, (size_t)R * G.sus_words) || dalloc(e, &G.det, (size_t)R * G.sus_words) || dalloc(e, &G.alist, (size_t)R * 2 * G.Npad) || dalloc(e, &G.items, (size_t)R * G.cap_items) || dalloc(e, &G.succ, (size_t)R * G.cap_succ) ||
+    if (dalloc(e, &G.hot, RN) || dalloc(e, &G.perm, RN) || dalloc(e, &G.rec, RN) ||
+        dalloc(e, &G.sus, (size_t)R * G.sus_words) || dalloc(e, &G.det, (size_t)R * G.sus_words) || dalloc(e, &G.alist, (size_t)R * 2 * G.n_seg * G.seg_cap) || dalloc(e, &G.seg_n, (size_t)R * 2 * G.n_seg) || dalloc(e, &G.items, (size_t)R * G.cap_items) || dalloc(e, &G.succ, (size_t)R * G.cap_succ) ||
         dalloc(e, &G.ev_key, (size_t)R * G.cap_events) || dalloc(e, &G.ev_agent, (size_t)R * G.cap_events) ||
         dalloc(e, &G.q_key, (size_t)R * 2 * G.cap_queue) || dalloc(e, &G.q_agent, (size_t)R * 2 * G.cap_queue) ||
         dalloc(e, &G.ctr, (size_t)R) || dalloc(e, &G.stats, (size_t)R * (cfg->max_days + 1) * G.row_len) ||
@@ -257,19 +285,18 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     CK(cudaMemset(G.stats, 0, sizeof(int32_t) * (size_t)R * (cfg->max_days + 1) * G.row_len));
     CK(cudaMemset(e->d_sched, 0, sizeof(rb_day_params) * ((size_t)cfg->max_days + 1)));
     // launch geometry: grid-stride kernels sized in multiples of the SM count
-    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
-    int sms = prop.multiProcessorCount;
     // the sweep fills the GPU exactly once: SW_CTAS_PER_SM resident CTAs per SM, shared out over the replicas (a grid a
     // little larger than one wave would run its tail on a nearly empty GPU)
-    // (`want`: a CTA per SW_THREADS list entries is the most a replica's active list can ever use)
-    int want = (G.Npad + SW_THREADS - 1) / SW_THREADS;
+    // (a warp per active-list segment is the most a replica can use)
+    int want = ((int)G.n_seg + SW_WARPS - 1) / SW_WARPS;
     int per_rep = sms * SW_CTAS_PER_SM / R; if (per_rep < 1) per_rep = 1;
     e->sweep_blocks = want < per_rep ? want : per_rep; if (e->sweep_blocks < 1) e->sweep_blocks = 1;
     e->list_blocks = sms * EX_CTAS_PER_SM / R; if (e->list_blocks < 2) e->list_blocks = 2;
     // k_resolve is a chain of dependent scattered accesses per infection: enough threads for one pass over the day's list
-    e->resolve_blocks = (int)((G.N / 128 + 255) / 256); if (e->resolve_blocks < e->list_blocks) e->resolve_blocks = e->list_blocks;
-    { int cap = sms * 16 / R; if (cap < 64) cap = 64; if (e->resolve_blocks > cap) e->resolve_blocks = cap; }
-    k_init<<<dim3(e->sweep_blocks, R), 256, 0, e->stream>>>(G); e->launches++;
+    e->resolve_blocks = resolve_grid(G.N, sms, 100, R);
+    k_init<<<dim3(e->sweep_blocks, R), 256, 0, e->stream>>>(G);
+    k_clear_lists<<<sms, 256, 0, e->stream>>>(G);
+    e->launches += 2;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     if (setup_groups(e, sms)) { rb_destroy(e); return 1; }
@@ -290,8 +317,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
 // with full-wave grids 154.9; 3 x 100 % 152.6; 4 x 50 % 153.0; 4 x 100 % 152.2; 8 x 50 % 156.0 -- the grids are
 // oversubscribed on purpose, a group in its latency-bound phase leaves its share of the SMs to the others.
 // RB_GROUPS / RB_GROUP_WAVE_PCT override (measurement aid).  Each group's grid covers `pct` % of one wave.
-static int setup_groups(rb_engine *e, int sms) {
-    const int R = e->G.R;
+static void group_config(int R, int *n_groups, int *wave_pct) {
     int ng = R >= 128 ? 4 : (R >= 32 ? 2 : 1), pct = R >= 128 ? 50 : 100;
     if (const char *s = getenv("RB_GROUPS")) ng = atoi(s);
     if (const char *s = getenv("RB_GROUP_WAVE_PCT")) pct = atoi(s);
@@ -299,19 +325,24 @@ static int setup_groups(rb_engine *e, int sms) {
     if (ng > MAX_GROUPS) ng = MAX_GROUPS;
     if (ng > R) ng = R;
     if (ng < 1) ng = 1;
+    *n_groups = ng; *wave_pct = pct;
+}
+static int setup_groups(rb_engine *e, int sms) {
+    const int R = e->G.R;
+    int ng, pct;
+    group_config(R, &ng, &pct);
     e->n_groups = ng;
     if (ng == 1) return 0;
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     const Eng &G = e->G;
-    const int want = (G.Npad + SW_THREADS - 1) / SW_THREADS;
+    const int want = ((int)G.n_seg + SW_WARPS - 1) / SW_WARPS;
     for (int g = 0; g < ng; g++) {
         ReplicaGroup &q = e->grp[g];
         q.r0 = (int)((long long)R * g / ng); q.R = (int)((long long)R * (g + 1) / ng) - q.r0;
         int per = sms * SW_CTAS_PER_SM * pct / 100 / q.R; if (per < 1) per = 1;
         q.sweep_blocks = want < per ? want : per;
         q.list_blocks = sms * EX_CTAS_PER_SM * pct / 100 / q.R; if (q.list_blocks < 2) q.list_blocks = 2;
-        q.resolve_blocks = (int)((G.N / 128 + 255) / 256); if (q.resolve_blocks < q.list_blocks) q.resolve_blocks = q.list_blocks;
-        { int cap = sms * 16 * pct / 100 / q.R; if (cap < 64) cap = 64; if (q.resolve_blocks > cap) q.resolve_blocks = cap; }
+        q.resolve_blocks = resolve_grid(G.N, sms, pct, q.R);
         CK(cudaStreamCreateWithFlags(&q.stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&q.ev_stagger, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&q.ev_join, cudaEventDisableTiming));
@@ -326,7 +357,9 @@ extern "C" int rb_reset(rb_engine *e, uint32_t seed) {
     e->day = 0;
     e->G.xepoch++;
     if (init_counters(e, seed)) return 1;
-    k_init<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G); e->launches++;
+    k_init<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G);
+    k_clear_lists<<<128, 256, 0, e->stream>>>(e->G);
+    e->launches += 2;
     if (e->has_ipc) {
         k_initial_state<<<e->G.R, 32, 0, e->stream>>>(e->G, e->ipc);
         k_rebuild_lists<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G);
@@ -351,41 +384,19 @@ extern "C" int rb_set_initial_state(rb_engine *e, const int32_t *ipc7) {
     return 0;
 }
 
-// Row guide of one table (DevTable::guide): rowfn(k) = first row r < nrows - 1 with k < cum24[r], else nrows - 1.
-static void build_row_guide(DevTable *h, int n_ages) {
-    const int shift = 24 - GUIDE_BITS;
-    for (int age = 0; age < n_ages; age++) {
-        const int nrows = h->n_rows[age];
-        if (nrows <= 0) continue;
-        const uint32_t *cum = h->cum24[age];
-        auto rowfn = [&](uint32_t k, int from) { int r = from; while (r < nrows - 1 && !(k < cum[r])) r++; return r; };
-        int r0 = 0;                                     // cum24 is non-decreasing: the first row only moves forward
-        for (uint32_t cell = 0; cell < (1u << GUIDE_BITS); cell++) {
-            const uint32_t lo = cell << shift, hi = lo + (1u << shift) - 1u;
-            r0 = rowfn(lo, r0);
-            const int r1 = rowfn(hi, r0);
-            uint32_t kind = 0, delta = 0;
-            if (r1 != r0) {
-                // lo < cum[r0] <= hi: the first boundary inside the cell.  One boundary only <=> its own value already maps to r1.
-                if (rowfn(cum[r0], r0) == r1 && r1 - r0 <= 15) { kind = 1; delta = (uint32_t)(r1 - r0); } else kind = 2;
-            }
-            h->guide[age][cell] = (uint16_t)((uint32_t)r0 | ((uint32_t)h->place[age][r0] << 7) | (delta << 10) | (kind << 14));
-        }
-    }
-}
-
+#define TABLE_HOST_BYTES (offsetof(DevTable, guide))      // what the host fills and uploads; the row guide is built on the device
 // A pinned staging buffer for table uploads: four slots used round-robin, each guarded by an event, so a run of uploads
 // (all mobility epochs of a schedule) is queued as asynchronous copies without a host-device synchronisation per table.
 static int stage_slot(rb_engine *e, DevTable **h, int *slot) {
     if (!e->h_stage) {
-        CK(cudaMallocHost((void **)&e->h_stage, sizeof(DevTable) * 4));
+        CK(cudaMallocHost((void **)&e->h_stage, TABLE_HOST_BYTES * 4));
         for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
         e->n_stage = 0;
     }
     const int k = e->n_stage & 3;
     if (e->n_stage >= 4) CK(cudaEventSynchronize(e->ev_stage[k]));     // the copy that last used this slot has left it
     e->n_stage++;
-    *h = e->h_stage + k; *slot = k;
+    *h = (DevTable *)((uint8_t *)e->h_stage + TABLE_HOST_BYTES * k); *slot = k;     // only the host-filled part of a DevTable is staged
     return 0;
 }
 
@@ -411,7 +422,7 @@ extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *
     }
     DevTable *h; int slot;
     if (stage_slot(e, &h, &slot)) return 1;
-    memset(h, 0, sizeof *h);
+    memset(h, 0, TABLE_HOST_BYTES);
     for (int age = 0; age < e->cfg.n_ages; age++) {
         h->n_rows[age] = n_rows[age];
         h->nr_contacts[age] = (float)nr_contacts[age];
@@ -441,9 +452,10 @@ extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *
             for (int b = 0, k = 0; b < 256; b++) {
                 const int limit = cls ? 5 : 100;
                 while (k < limit && !(h->ncdf[age][cls][k] > (double)b / 256.0)) k++;
-                h->nguide[age][cls][b] = (uint8_t)k;
+                // every u of the cell, b/256 <= u < (b+1)/256, draws k iff cdf[k] reaches the cell's end (or k is the cap)
+                const bool exact = k >= limit || h->ncdf[age][cls][k] >= (double)(b + 1) / 256.0;
+                h->nguide[age][cls][b] = (uint8_t)(k | (exact ? 0 : 128));
             }
-    build_row_guide(h, e->cfg.n_ages);
     DevTable *d = e->tables[epoch];
     if (!d) {
         if (dalloc(e, &d, 1)) return 1;
@@ -451,9 +463,11 @@ extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *
         CK(cudaMemcpyAsync(e->d_tables + epoch, &e->tables[epoch], sizeof(DevTable *), cudaMemcpyHostToDevice, e->stream));
     }
     // stream order keeps the copy behind every kernel of earlier steps (the replica-group streams join e->stream)
-    CK(cudaMemcpyAsync(d, h, sizeof(DevTable), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(d, h, TABLE_HOST_BYTES, cudaMemcpyHostToDevice, e->stream));
     CK(cudaEventRecord(e->ev_stage[slot], e->stream));
-    e->h2d_bytes += (int64_t)sizeof(DevTable);
+    k_build_guide<<<e->cfg.n_ages, 256, 0, e->stream>>>(d, e->cfg.n_ages); e->launches++;
+    CK(cudaGetLastError());
+    e->h2d_bytes += (int64_t)TABLE_HOST_BYTES;
     return 0;
 }
 
@@ -1109,9 +1123,10 @@ extern "C" int rb_load_state(rb_engine *e, const void *in, int64_t n_bytes) {
     CK(cudaStreamSynchronize(e->stream));
     const uint8_t *o = (const uint8_t *)in + sizeof h;
     for (const StatePart &p : state_parts(e)) { CK(cudaMemcpy(p.dev, o, p.bytes, cudaMemcpyHostToDevice)); o += p.bytes; }
-    // both list counters to zero, then list `lsel` of every replica from the packed words
-    CK(cudaMemset2DAsync(&e->G.ctr[0].n_list[0], sizeof(RepCtr), 0, sizeof(uint32_t) * 2, (size_t)e->G.R, e->stream));
-    k_rebuild_lists<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G); e->launches++;
+    // every segment counter to zero, then lists `lsel` of every replica from the packed words
+    k_clear_lists<<<128, 256, 0, e->stream>>>(e->G);
+    k_rebuild_lists<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G);
+    e->launches += 2;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     e->day = h.day; e->cfg.seed = h.seed;

@@ -94,6 +94,33 @@ __global__ void k_initial_state(Eng G, Ipc P) {
     for (int32_t i = 0; i < P.confirmed; i++) c->counts[RB_A_ALL_DETECTED][(100 + i) % 100] += 1;
 }
 
+// ---------------------------------------------------------------- row guide of a contact table
+// DevTable::guide from cum24 / place, one CTA per age.  rowfn(k) = first row r < nrows - 1 with k < cum24[r], else nrows - 1.
+__device__ __forceinline__ int guide_rowfn(const uint32_t *cum, int nrows, uint32_t k) {
+    int lo = 0, hi = nrows - 1;                       // cum24 is non-decreasing: binary search for the first row with k < cum[r]
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (k < cum[mid]) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+__global__ void k_build_guide(DevTable *tb, int n_ages) {
+    const int age = blockIdx.x;
+    if (age >= n_ages) return;
+    const int nrows = tb->n_rows[age];
+    if (nrows <= 0) return;
+    const uint32_t *cum = tb->cum24[age];
+    const int shift = 24 - GUIDE_BITS;
+    for (uint32_t cell = threadIdx.x; cell < (1u << GUIDE_BITS); cell += blockDim.x) {
+        const uint32_t lo = cell << shift, hi = lo + (1u << shift) - 1u;
+        const int r0 = guide_rowfn(cum, nrows, lo), r1 = guide_rowfn(cum, nrows, hi);
+        uint32_t delta = 0, blow = 0, place1 = 0;
+        if (r1 != r0) {
+            // lo < cum[r0] <= hi: the first boundary inside the cell.  One boundary only <=> its own value already maps to r1.
+            if (guide_rowfn(cum, nrows, cum[r0]) == r1 && r1 - r0 <= 14) { delta = (uint32_t)(r1 - r0); blow = cum[r0] - lo; place1 = tb->place[age][r1]; }
+            else delta = 15;
+        }
+        tb->guide[age][cell] = (uint32_t)r0 | ((uint32_t)tb->place[age][r0] << 7) | (delta << 10) | (place1 << 14) | (blow << 17);
+    }
+}
+
 // ---------------------------------------------------------------- misc kernels
 __global__ void k_init(Eng G) {
     const int r = blockIdx.y;

@@ -57,7 +57,7 @@ enum { EV_HOSP_CLAIM = 0, EV_WARD_RELEASE = 1, EV_TO_ICU = 2, EV_ICU_RELEASE = 3
 #define NEG_INF (-(1 << 29))
 
 #ifndef GUIDE_BITS
-#define GUIDE_BITS 10        // cells per age in the row guide (2 KB per age: the table of one epoch stays L1-resident)
+#define GUIDE_BITS 12        // 2^GUIDE_BITS cells per age in the row guide (>= 9: the boundary's low bits must fit the entry); measured 9 / 10 / 11: 721 / 645 / 607 us on the peak day
 #endif
 struct DevTable {
     int32_t n_rows[RB_MAX_AGES];
@@ -71,12 +71,15 @@ struct DevTable {
     uint8_t place[RB_MAX_AGES][RB_MAX_ROWS];
     uint8_t lo_age[RB_MAX_AGES][RB_MAX_ROWS], hi_age[RB_MAX_AGES][RB_MAX_ROWS];
     uint8_t susc_uniform[RB_MAX_AGES][RB_MAX_ROWS];   // susceptibility identical for every age of the row's band
-    // O(1) row pick (get_one_contact, main.pyx:1290-1304): the 24-bit uniform's top GUIDE_BITS bits select a cell; the
-    // entry says which row the cell's first value maps to, that row's place, and whether the whole cell maps to it
-    // (kind 0), or everything from cum24[row0] on maps to row0 + delta (kind 1: one boundary inside the cell, rows of zero
-    // probability in between), or the cell holds several boundaries and the search walks on from row0 (kind 2, rare)
-    uint16_t guide[RB_MAX_AGES][1 << GUIDE_BITS];     // row0 7b | place0 3b << 7 | delta 4b << 10 | kind 2b << 14
-    uint8_t nguide[RB_MAX_AGES][2][256];              // first k with ncdf[k] > b/256: start of the contact-count search
+    uint8_t nguide[RB_MAX_AGES][2][256];              // k0 = first k with ncdf[k] > b/256: start of the contact-count search; bit 7: the cell holds a boundary, search on from k0
+    // ---- everything above is filled by the host (rb_set_contact_table); the row guide below is derived from cum24 / place
+    // on the device (k_build_guide), so it never crosses PCIe
+    // O(1) row pick (get_one_contact, main.pyx:1290-1304): the 24-bit uniform's top GUIDE_BITS bits select a cell, and
+    // ONE 4-byte entry answers for the whole cell: row0 = row of the cell's first value (7 b), its place (3 b << 7),
+    // delta (4 b << 10): 0 = every value of the cell maps to row0; 1..14 = one boundary inside the cell, values whose low
+    // bits are >= blow (<< 17, the boundary's low 24 - GUIDE_BITS bits) map to row0 + delta, whose place is place1
+    // (3 b << 14; the rows in between have probability zero); 15 = several boundaries, the search walks on from row0 (rare).
+    uint32_t guide[RB_MAX_AGES][1 << GUIDE_BITS];
 };
 
 struct Attempt { uint32_t cand, parent; unsigned long long key; };
@@ -106,14 +109,13 @@ struct RepCtr {
     uint32_t n_queue, qsel;
     uint32_t n_queue_prev;                        // size of the queue drained yesterday (normalises tracing keys for sorting)
     uint32_t any_vacc;                            // set once the first vaccination programme starts
-    uint32_t lsel;                                // active list in force today: the sweep reads list lsel and writes list lsel ^ 1
+    uint32_t lsel;                                // active lists in force today: the sweep reads lists lsel and writes lists lsel ^ 1
     uint32_t ct_ever;                             // contact tracing has been on at some point: detections may reach agents behind the list's back
     uint32_t n_q_base;                            // entries contact tracing put into tomorrow's queue before the sweep
     uint32_t drained;                             // tomorrow's queue was already drained by k_resolve (detections parked in drain_det)
     int32_t ct_cases;
     int32_t vacc_cursor[RB_MAX_VACC];
     // ---- atomics of the grid kernels, one line per group
-    alignas(128) uint32_t n_list[2];              // entries of the two active lists
     alignas(128) uint32_t n_items;
     alignas(128) uint32_t n_succ;
     alignas(128) int32_t exposed_per_day;
@@ -139,12 +141,20 @@ struct Eng {
     int32_t N, Npad, n_ages, n_groups, n_variants, R, max_days, row_len, n_import_classes, fhalf;
     uint32_t cap_items, cap_succ, cap_events, cap_queue;
     uint32_t *hot;
+    uint32_t *perm;                                // [R][Npad] slot in the replica's sweep order, valid once the agent has been infected
     AgentRec *rec;
     uint32_t *sus;                                 // [R][sus_words] 1 bit per agent: still SUSCEPTIBLE (L2-resident gather target)
     int32_t sus_words;
     uint32_t *det;                                 // [R][sus_words] 1 bit per agent: detected by a test-queue drain (the sweep consults it once contact tracing has been on)
-    uint2 *alist;                                  // [R][2][cap_list] active lists: (agent, copy of its packed word with CURRENT day counters)
-    uint32_t cap_list;
+    // Active lists: (agent, copy of its packed word with CURRENT day counters).  Every replica has n_seg segments, agent
+    // a always lives in segment a % n_seg (so a segment can never hold more than seg_cap = ceil(N / n_seg) entries), and
+    // one warp of the sweep owns a whole segment while it runs.  A segment is filled from BOTH ends: the owning warp
+    // writes the survivors of its pass to the front, behind a counter it keeps in a register (no atomics on the sweep's
+    // hot loop); everybody else -- the sweep's own slow stage, k_resolve and the imports with their new infections --
+    // appends at the back with an atomic on the segment's second counter.  The two ends cannot meet.
+    uint2 *alist;                                  // [R][2][n_seg][seg_cap]
+    uint2 *seg_n;                                  // [R][2][n_seg] entries at the front (.x) / at the back (.y) of each segment
+    uint32_t n_seg, seg_cap;
     uint2 *items;
     Attempt *succ;
     unsigned long long *ev_key; int32_t *ev_agent;
@@ -216,8 +226,15 @@ __device__ __forceinline__ int age_in_band(const Eng &G, int32_t a, int lo, int 
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(&G.age_start[mid]) <= a) lo = mid; else hi = mid; }
     return lo;
 }
-__device__ __forceinline__ uint32_t sweep_pos(const Eng &G, const RepCtr *c, uint32_t a) {
-    uint32_t s = feistel(a, (uint32_t)G.N, G.fhalf, c->fkey[0], c->fkey[1], c->fkey[2], c->fkey[3]);
+// Position of agent a in today's sweep (main.pyx:1436, 1988): its slot in the replica's fixed random order, rotated by
+// today's start.  The slot -- a keyed Feistel permutation, ~45 instructions -- does not depend on the day, so it is
+// computed once, when the agent is infected (device_infect), and kept in `perm`: only infected agents ever need a sweep
+// position (capacity events, test-queue entries, transmissions).
+__device__ __forceinline__ uint32_t sweep_slot(const Eng &G, const RepCtr *c, uint32_t a) {
+    return feistel(a, (uint32_t)G.N, G.fhalf, c->fkey[0], c->fkey[1], c->fkey[2], c->fkey[3]);
+}
+__device__ __forceinline__ uint32_t sweep_pos(const Eng &G, int r, const RepCtr *c, uint32_t a) {
+    const uint32_t s = G.perm[(size_t)r * G.Npad + a];
     return s >= c->start ? s - c->start : s + (uint32_t)G.N - c->start;
 }
 // A test-queue drain detected agent a (person_detect, main.pyx:294-298).  The sweep keeps its own copies of the active
@@ -245,6 +262,20 @@ __device__ __forceinline__ int symptom_severity(const rb_variant *v, int age, fl
     if (val < (cc * sc) * syc) return RB_CRITICAL;
     if (val < sc * syc) return RB_SEVERE;
     return RB_MILD;
+}
+
+// Segment s of list `which` of replica r, and its two entry counters.
+__device__ __forceinline__ uint2 *seg_ptr(const Eng &G, int r, uint32_t which, uint32_t s) {
+    return G.alist + (((size_t)r * 2 + which) * G.n_seg + s) * G.seg_cap;
+}
+__device__ __forceinline__ uint2 *seg_count(const Eng &G, int r, uint32_t which, uint32_t s) {
+    return G.seg_n + ((size_t)r * 2 + which) * G.n_seg + s;
+}
+// One more entry at the back of agent a's segment (new infections, the sweep's slow stage, list rebuilds).
+__device__ __forceinline__ void list_add(const Eng &G, int r, RepCtr *c, uint32_t which, uint32_t a, uint32_t w) {
+    const uint32_t s = a % G.n_seg;
+    const uint32_t k = atomicAdd(&seg_count(G, r, which, s)->y, 1u);
+    if (k < G.seg_cap) seg_ptr(G, r, which, s)[G.seg_cap - 1u - k] = make_uint2(a, w); else set_problem(c, RB_OTHER_FAILURE);
 }
 
 // person_infect, main.pyx:209-235 + Population.infect :1576-1582.  `src_h` = packed word of the infector
@@ -282,16 +313,9 @@ __device__ void device_infect(const Eng &G, int r, RepCtr *c, int32_t t, int32_t
     if (fresh) nh |= H_FRESH;
     if (has_list) nh |= H_LIST;      // person_infect, main.pyx:227-233: an infectee list only under contact tracing
     G.hot[base + t] = nh;
+    G.perm[base + t] = sweep_slot(G, c, (uint32_t)t);
     atomicAnd(&G.sus[(size_t)r * G.sus_words + (t >> 5)], ~(1u << (t & 31)));
-    if (list >= 0 && owns(G, (uint32_t)t)) {      // from now on the sweep visits this agent: one warp-aggregated append
-        const unsigned am = __activemask();
-        const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
-        uint32_t b = 0;
-        if (lane == leader) b = atomicAdd(&c->n_list[list], (uint32_t)__popc(am));
-        b = __shfl_sync(am, b, leader) + __popc(am & ((1u << lane) - 1u));
-        if (b < G.cap_list) G.alist[((size_t)r * 2 + list) * G.cap_list + b] = make_uint2((uint32_t)t, nh);
-        else set_problem(c, RB_OTHER_FAILURE);
-    }
+    if (list >= 0 && owns(G, (uint32_t)t)) list_add(G, r, c, (uint32_t)list, (uint32_t)t, nh);      // from now on the sweep visits this agent
     count_add(c, RB_A_SUSCEPTIBLE, age, -1);
     count_add(c, RB_A_INFECTED, age, 1);
     count_add(c, RB_A_ALL_INFECTED, age, 1);

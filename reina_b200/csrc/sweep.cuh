@@ -7,14 +7,16 @@
 // ---------------------------------------------------------------- k_sweep
 // The daily sweep = Context._iterate_people / _process_person / person_advance (main.pyx:1968-1992, 395-438).
 //
-// The reference walks all N agents every day to find the few per cent that are infected.  Here every replica keeps a
-// dense ACTIVE LIST: one 8-byte entry (agent, copy of its packed word with today's day counters) per agent that is
-// infected, or removed and not yet counted in R.  The sweep streams the list coalesced, advances the day counters in the
-// copy and writes the survivors, compacted, to the second list (read tomorrow); `hot`, the authoritative packed word
-// that every other kernel gathers, is touched only when an agent changes state.  New infections are appended by
-// k_resolve / the imports (device_infect).  The order of the list is arbitrary and differs from run to run; nothing
-// observable depends on it, because every order-dependent step of the reference is keyed on the agent's sweep position
-// and every draw on (seed, agent, day, purpose).
+// The reference walks all N agents every day to find the few per cent that are infected.  Here every replica keeps
+// dense ACTIVE LISTS: one 8-byte entry (agent, copy of its packed word with today's day counters) per agent that is
+// infected, or removed and not yet counted in R, in n_seg segments (agent a lives in segment a % n_seg for good).  A warp
+// of the sweep owns whole segments: it streams segment s of today's buffer coalesced, advances the day counters in the
+// copies and writes the survivors, compacted, to segment s of tomorrow's buffer behind a counter it keeps in a register
+// -- no atomics, no other warp ever touches that segment during the sweep.  `hot`, the authoritative packed word that
+// every other kernel gathers, is touched only when an agent changes state.  New infections are appended by k_resolve /
+// the imports (device_infect -> list_add).  The order inside a segment is arbitrary and differs from run to run;
+// nothing observable depends on it, because every order-dependent step of the reference is keyed on the agent's sweep
+// position and every draw on (seed, agent, day, purpose).
 //
 // Work flows through two warp-private shared-memory rings, each drained only in full batches of 32, so the two heavy
 // stages execute on dense warps and no block-level barrier exists anywhere:
@@ -31,7 +33,7 @@
 #define SW_WARPS (SW_THREADS / 32)
 #define SW_RCAP 64
 #ifndef SW_CTAS_PER_SM
-#define SW_CTAS_PER_SM 10
+#define SW_CTAS_PER_SM 9      // 56 registers, no spills (10 CTAs = 48 registers spills the stage state)
 #endif
 
 struct WarpRings {
@@ -46,17 +48,14 @@ __device__ __forceinline__ uint32_t ring_push(uint32_t *ra, uint32_t *rb, uint32
     return tail + __popc(m);
 }
 
-// warp-aggregated append of (a, w) for the lanes with `want` to tomorrow's active list
-__device__ __forceinline__ void list_append(const Eng &G, RepCtr *c, uint2 *next, uint32_t *n_next, bool want, uint32_t a, uint32_t w, int lane) {
+// The lanes with `want` append (a, w) to the segment this warp owns: `out_n` is the warp's private entry counter.
+__device__ __forceinline__ void seg_append(const Eng &G, RepCtr *c, uint2 *out, uint32_t &out_n, bool want, uint32_t a, uint32_t w, int lane) {
     const uint32_t m = __ballot_sync(0xffffffffu, want);
-    if (!m) return;
-    uint32_t b = 0;
-    if (lane == 0) b = atomicAdd(n_next, (uint32_t)__popc(m));
-    b = __shfl_sync(0xffffffffu, b, 0);
     if (want) {
-        const uint32_t p = b + __popc(m & ((1u << lane) - 1u));
-        if (p < G.cap_list) next[p] = make_uint2(a, w); else set_problem(c, RB_OTHER_FAILURE);
+        const uint32_t p = out_n + __popc(m & ((1u << lane) - 1u));
+        if (p < G.seg_cap) out[p] = make_uint2(a, w); else set_problem(c, RB_OTHER_FAILURE);
     }
+    out_n += __popc(m);
 }
 
 // Where the sweep puts what other kernels (and, in population-sharded mode, other ranks) consume.  Single GPU: the
@@ -85,7 +84,7 @@ __device__ __forceinline__ SweepOut sweep_out(const Eng &G, int r, RepCtr *c) {
 // stage E: get_exposed_people / get_nr_contacts (main.pyx:936-955, 1308-1320) + work-item emission
 __device__ __forceinline__ void stage_expose(const Eng &G, int r, RepCtr *c, RepCtr *cd, const DevTable *tb, const WarpRings &W, uint32_t head, uint32_t m,
                                              uint2 *items, int lane) {
-    uint32_t cnt = 0, ncont = 0, desc = 0, a = 0;
+    uint32_t ncont = 0, desc = 0, a = 0;
     if ((uint32_t)lane < m) {
         a = W.ea[(head + lane) & (SW_RCAP - 1)];
         desc = W.ed[(head + lane) & (SW_RCAP - 1)];
@@ -98,50 +97,40 @@ __device__ __forceinline__ void stage_expose(const Eng &G, int r, RepCtr *c, Rep
             const int cls = (desc >> 22) & 1u;
             u32x4 x = philox(c->seed, a, (uint32_t)c->day, PU_NCONTACT, 0);
             const double u = u01d(x.x, x.y);
-            // n = first k with u < cdf[k] (k = limit if none); entries below nguide[u's top 8 bits] cannot match
+            // n = first k with u < cdf[k] (k = limit if none); nguide[u's top 8 bits] = the answer for most cells, else where to start
             const double *cdf = tb->ncdf[age][cls];
             const int limit = cls ? 5 : 100;
-            int k = tb->nguide[age][cls][x.x >> 24];
-            while (k < limit && !(u < __ldg(&cdf[k]))) k++;
+            const uint32_t ng = tb->nguide[age][cls][x.x >> 24];
+            int k = (int)(ng & 127u);
+            if (ng & 128u) while (k < limit && !(u < __ldg(&cdf[k]))) k++;
             ncont = (uint32_t)k;
-            cnt = (ncont + 3u) >> 2;          // work items are groups of four contact slots (they share one Philox block)
             desc = (desc & ~(1u << 22)) | ((uint32_t)age << 7);
         }
     }
-    uint32_t incl = cnt;
+    // work items are groups of four contact slots (they share one Philox block).  One scan for both totals: items in
+    // the low half (<= 32 x 25), contacts in the high half (<= 32 x 100)
+    const uint32_t cnt = (ncont + 3u) >> 2;
+    uint32_t incl = cnt | (ncont << 16);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31), wtot = tot & 0xffffu;
     if (wtot == 0) return;
-    const uint32_t excl = incl - cnt;
     uint32_t gbase = 0;
-    uint32_t ctot = ncont;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ctot += __shfl_xor_sync(0xffffffffu, ctot, o);
-    if (lane == 31) { gbase = atomicAdd(&c->n_items, wtot); atomicAdd(&cd->exposed_per_day, (int)ctot); }
+    if (lane == 31) { gbase = atomicAdd(&c->n_items, wtot); atomicAdd(&cd->exposed_per_day, (int)(tot >> 16)); }
     gbase = __shfl_sync(0xffffffffu, gbase, 31);
     if (gbase + wtot > G.cap_items) { if (lane == 0) set_problem(cd, RB_OTHER_FAILURE); return; }
-    for (uint32_t t0 = 0; t0 < wtot; t0 += 32) {
-        const uint32_t t = t0 + lane;
-        int lo = 0;     // owner = largest lane whose exclusive prefix is <= t
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            uint32_t e = __shfl_sync(0xffffffffu, excl, (lo + step) & 31);
-            if (lo + step < 32 && e <= t) lo += step;
-        }
-        const uint32_t oa = __shfl_sync(0xffffffffu, a, lo), od = __shfl_sync(0xffffffffu, desc, lo), oe = __shfl_sync(0xffffffffu, excl, lo);
-        const uint32_t on = __shfl_sync(0xffffffffu, ncont, lo);
-        if (t < wtot) {
-            const uint32_t g = t - oe, left = on - 4u * g;            // group index, contacts from this group on
-            items[gbase + t] = make_uint2(oa, od | g | (((left < 4u ? left : 4u) - 1u) << 5));
-        }
+    // every lane writes the items of its own agent (1-2 for most, 25 at the cap): the warp runs as long as its busiest lane
+    uint2 *mine = items + gbase + ((incl & 0xffffu) - cnt);
+    for (uint32_t g = 0; g < cnt; g++) {
+        const uint32_t left = ncont - 4u * g;            // contacts from this group on
+        mine[g] = make_uint2(a, desc | g | (((left < 4u ? left : 4u) - 1u) << 5));
     }
 }
 
-__device__ __forceinline__ void emit_event(const Eng &G, const SweepOut &O, RepCtr *c, int32_t a, int type) {
+__device__ __forceinline__ void emit_event(const Eng &G, int r, const SweepOut &O, RepCtr *c, int32_t a, int type) {
     uint32_t idx = atomicAdd(&O.cd->n_events, 1u);
     if (idx < O.cap_ev) {
-        O.ev_key[idx] = ((unsigned long long)sweep_pos(G, c, (uint32_t)a) << 2) | (unsigned)type;
+        O.ev_key[idx] = ((unsigned long long)sweep_pos(G, r, c, (uint32_t)a) << 2) | (unsigned)type;
         O.ev_agent[idx] = a;
     } else set_problem(O.cd, RB_OTHER_FAILURE);
 }
@@ -191,7 +180,7 @@ __device__ __forceinline__ uint32_t transition(const Eng &G, int r, RepCtr *c, c
                 h |= H_QUEUED;
                 uint32_t idx = atomicAdd(&cd->n_newq, 1u);
                 if (idx < O.cap_q) {
-                    O.q_key[idx] = QKEY_SWEEP | sweep_pos(G, c, (uint32_t)a);
+                    O.q_key[idx] = QKEY_SWEEP | sweep_pos(G, r, c, (uint32_t)a);
                     O.q_agent[idx] = a;
                 } else set_problem(cd, RB_OTHER_FAILURE);
             }
@@ -203,7 +192,7 @@ __device__ __forceinline__ uint32_t transition(const Eng &G, int r, RepCtr *c, c
             count_add(cd, RB_A_INFECTED, age, -1); count_add(cd, RB_A_DEAD, age, 1); count_add(cd, RB_A_NON_HOSPITAL_DEATHS, age, 1);
         } else if (sev >= RB_SEVERE) {               // person_hospitalize, main.pyx:321-338: the bed claim is an event
             if (!(h & H_DET)) { h |= H_DET; count_add(cd, RB_A_DETECTED, age, 1); count_add(cd, RB_A_ALL_DETECTED, age, 1); }
-            emit_event(G, O, c, a, EV_HOSP_CLAIM);
+            emit_event(G, r, O, c, a, EV_HOSP_CLAIM);
             extra = H_PEND;
         } else {                                     // person_recover, main.pyx:315-318
             h = H_SET_STATE(h, RB_RECOVERED) & ~H_LIST;
@@ -220,7 +209,7 @@ __device__ __forceinline__ uint32_t transition(const Eng &G, int r, RepCtr *c, c
             if (sev == RB_FATAL) { h = H_SET_STATE(h, RB_DEAD) & ~H_LIST; count_add(cd, RB_A_DEAD, age, 1); count_add(cd, RB_A_NON_HOSPITAL_DEATHS, age, 1); }
             else { h = H_SET_STATE(h, RB_RECOVERED) & ~H_LIST; count_add(cd, RB_A_RECOVERED, age, 1); }
         }
-        emit_event(G, O, c, a, type);
+        emit_event(G, r, O, c, a, type);
     }
     lw = h | extra;
     return h;
@@ -229,7 +218,7 @@ __device__ __forceinline__ uint32_t transition(const Eng &G, int r, RepCtr *c, c
 // stage T on one batch of ring T.  Every lane first fetches the authoritative word (flags may have changed behind the
 // list's back: detected / queued / vaccinated) and merges the list copy's current day counters into it.
 __device__ __forceinline__ void stage_slow(const Eng &G, int r, RepCtr *c, RepCtr *cd, const WarpRings &W, uint32_t head, uint32_t m,
-                                           uint2 *next, uint32_t *n_next, int lane) {
+                                           uint32_t next, int lane) {
     const SweepOut O = sweep_out(G, r, c);     // resolved here, not in the caller: the streaming loop stays light on registers
     const size_t base = (size_t)r * G.Npad;
     const bool on = (uint32_t)lane < m;
@@ -263,7 +252,7 @@ __device__ __forceinline__ void stage_slow(const Eng &G, int r, RepCtr *c, RepCt
         for (int o = 16; o > 0; o >>= 1) infected_others += __shfl_xor_sync(0xffffffffu, infected_others, o);
         if (lane == 0) { atomicAdd(&cd->total_infectors, __popc(rm)); if (infected_others) atomicAdd(&cd->total_infections, infected_others); }
     }
-    list_append(G, cd, next, n_next, keep, a, lw, lane);
+    if (keep) list_add(G, r, cd, next, a, lw);      // back of the agent's own segment in tomorrow's buffer (whoever owns its front)
     if (O.upd) {      // sharded mode: the other ranks' copies of this agent learn the new state and flags from the log
         const uint32_t mk = __ballot_sync(0xffffffffu, changed);
         uint32_t b = 0;
@@ -297,9 +286,9 @@ __device__ __forceinline__ void stage_entry(const Eng &G, uint32_t &w, bool &kee
     if (dl == 0) want_t = true; else keep = true;
 }
 
-// One loop per warp over its share of the replica's active list, 32 entries per step, the next step's entries loaded
-// ahead.  Every stage is instantiated exactly ONCE (the heavy stages are thousands of instructions each; a second inlined
-// copy pushes the loop out of the instruction cache).
+// One loop per warp over the segments it owns, 32 entries per step, the next step's entries loaded ahead.  Every stage
+// is instantiated exactly ONCE (the heavy stages are thousands of instructions each; a second inlined copy pushes the
+// loop out of the instruction cache).
 __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
     __shared__ WarpRings s_rings[SW_WARPS];
     const int r = blockIdx.y + G.r0;
@@ -310,39 +299,50 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
     WarpRings &W = s_rings[warp];
     RepCtr *cd = !G.xbuf ? c : xslot_of(G, G.rank, c->day).hdr;      // counters the sweep adds to
     const uint32_t cur = c->lsel;
-    const uint32_t n = min(c->n_list[cur], G.cap_list);
-    const uint2 *list = G.alist + ((size_t)r * 2 + cur) * G.cap_list;
-    uint2 *next = G.alist + ((size_t)r * 2 + (cur ^ 1u)) * G.cap_list;
-    uint32_t *n_next = &c->n_list[cur ^ 1u];
-    const uint32_t stride = gridDim.x * SW_WARPS * 32u;
+    const uint32_t n_warps = gridDim.x * SW_WARPS;
     uint32_t e_head = 0, e_tail = 0, t_head = 0, t_tail = 0;
 
-    uint32_t i = (blockIdx.x * SW_WARPS + warp) * 32u + lane;
-    uint2 ent = make_uint2(0u, 0u);
-    if (i < n) ent = __ldcs(&list[i]);
-    for (uint32_t i0 = i - lane; i0 < n; i0 += stride) {
-        const bool valid = i < n;
-        const uint2 cur_ent = ent;
-        i += stride;
-        if (i < n) ent = __ldcs(&list[i]);              // next step's entry: in flight while this one is processed
-        bool keep = false, want_e = false, want_t = false;
-        uint32_t w = cur_ent.y, desc = 0;
-        if (valid) stage_entry(G, w, keep, want_e, want_t, desc);
-        list_append(G, cd, next, n_next, keep, cur_ent.x, w, lane);
-        e_tail = ring_push(W.ea, W.ed, e_tail, want_e, cur_ent.x, desc, lane);
-        t_tail = ring_push(W.ta, W.tw, t_tail, want_t, cur_ent.x, w, lane);
-        __syncwarp();
-        if (e_tail - e_head >= 32) { stage_expose(G, r, c, cd, tb, W, e_head, 32, items, lane); e_head += 32; }
-        if (t_tail - t_head >= 32) { stage_slow(G, r, c, cd, W, t_head, 32, next, n_next, lane); t_head += 32; }
-        __syncwarp();
-    }
-    // whatever is left in the rings (less than a full batch each); the stages above are the only instances, so the
-    // remainders go through the same code
-    while (e_tail != e_head || t_tail != t_head) {
-        const uint32_t e_av = e_tail - e_head, t_av = t_tail - t_head;
-        if (e_av) { const uint32_t m = min(32u, e_av); stage_expose(G, r, c, cd, tb, W, e_head, m, items, lane); e_head += m; }
-        if (t_av) { const uint32_t m = min(32u, t_av); stage_slow(G, r, c, cd, W, t_head, m, next, n_next, lane); t_head += m; }
-        __syncwarp();
+    // One pass per owned segment plus a final pass that only drains the rings: the stages have exactly one call site each.
+    uint2 cnt_next = make_uint2(0u, 0u);      // the counters of the next segment are fetched while this one is processed
+    if (blockIdx.x * SW_WARPS + warp < G.n_seg) cnt_next = *seg_count(G, r, cur, blockIdx.x * SW_WARPS + warp);
+    for (uint32_t seg = blockIdx.x * SW_WARPS + warp; ; seg += n_warps) {
+        const bool tail = seg >= G.n_seg;
+        const uint2 cnt = cnt_next;
+        cnt_next = make_uint2(0u, 0u);
+        if (seg + n_warps < G.n_seg) cnt_next = *seg_count(G, r, cur, seg + n_warps);
+        const uint32_t nf = min(cnt.x, G.seg_cap), n = min(cnt.x + cnt.y, G.seg_cap);
+        const uint2 *in = seg_ptr(G, r, cur, tail ? 0u : seg);
+        uint2 *out = seg_ptr(G, r, cur ^ 1u, tail ? 0u : seg);
+        uint32_t out_n = 0;
+        // entry i of the segment: the front part, then the back part (it ends at the segment's end; its order is irrelevant)
+        const uint32_t gap = G.seg_cap - n;
+        auto entry = [&](uint32_t i) { return __ldcs(&in[i < nf ? i : i + gap]); };
+        uint2 ent = make_uint2(0u, 0u);
+        if ((uint32_t)lane < n) ent = entry(lane);
+        uint32_t i0 = 0;
+        bool again;
+        do {
+            if (i0 < n) {
+                const bool valid = i0 + lane < n;
+                const uint2 cur_ent = ent;
+                if (i0 + 32 + lane < n) ent = entry(i0 + 32 + lane);      // next step's entry: in flight while this one is processed
+                bool keep = false, want_e = false, want_t = false;
+                uint32_t w = cur_ent.y, desc = 0;
+                if (valid) stage_entry(G, w, keep, want_e, want_t, desc);
+                seg_append(G, cd, out, out_n, keep, cur_ent.x, w, lane);
+                e_tail = ring_push(W.ea, W.ed, e_tail, want_e, cur_ent.x, desc, lane);
+                t_tail = ring_push(W.ta, W.tw, t_tail, want_t, cur_ent.x, w, lane);
+                __syncwarp();
+            }
+            const uint32_t e_av = e_tail - e_head, t_av = t_tail - t_head;
+            if (e_av >= 32 || (tail && e_av)) { const uint32_t m = min(32u, e_av); stage_expose(G, r, c, cd, tb, W, e_head, m, items, lane); e_head += m; }
+            if (t_av >= 32 || (tail && t_av)) { const uint32_t m = min(32u, t_av); stage_slow(G, r, c, cd, W, t_head, m, cur ^ 1u, lane); t_head += m; }
+            __syncwarp();
+            i0 += 32;
+            again = tail ? (e_tail != e_head || t_tail != t_head) : i0 < n;
+        } while (again);
+        if (tail) break;
+        if (lane == 0) seg_count(G, r, cur ^ 1u, seg)->x = out_n;     // front of tomorrow's segment; its back fills by atomics
     }
 }
 
@@ -354,13 +354,19 @@ __global__ void k_flush_lists(Eng G) {
     const int r = blockIdx.y;
     const RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
-    const uint32_t cur = c->lsel, n = min(c->n_list[cur], G.cap_list);
-    const uint2 *list = G.alist + ((size_t)r * 2 + cur) * G.cap_list;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint2 e = list[i];
-        if ((e.y & H_PEND) || H_STATE(e.y) >= RB_RECOVERED) continue;
-        const uint32_t h = G.hot[base + e.x];
-        G.hot[base + e.x] = (h & ~(H_DAYS_MASK | H_FRESH)) | (e.y & (H_DAYS_MASK | H_FRESH));
+    const uint32_t cur = c->lsel;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); seg < G.n_seg; seg += n_warps) {
+        const uint2 cnt = *seg_count(G, r, cur, seg);
+        const uint32_t nf = min(cnt.x, G.seg_cap), n = min(cnt.x + cnt.y, G.seg_cap);
+        const uint2 *in = seg_ptr(G, r, cur, seg);
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint2 e = in[i < nf ? i : i + (G.seg_cap - n)];
+            if ((e.y & H_PEND) || H_STATE(e.y) >= RB_RECOVERED) continue;
+            const uint32_t h = G.hot[base + e.x];
+            G.hot[base + e.x] = (h & ~(H_DAYS_MASK | H_FRESH)) | (e.y & (H_DAYS_MASK | H_FRESH));
+        }
     }
 }
 // k_rebuild_lists: the active list of every replica from `hot` (after rb_load_state / set_initial_state): everybody who
@@ -371,19 +377,20 @@ __global__ void k_rebuild_lists(Eng G) {
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
     const uint32_t cur = c->lsel;
-    uint2 *list = G.alist + ((size_t)r * 2 + cur) * G.cap_list;
-    const int lane = threadIdx.x & 31;
-    const int n_pad = (G.N + 31) & ~31;
-    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_pad; a += gridDim.x * blockDim.x) {
-        uint32_t h = 0; bool want = false;
-        if (a < G.N && owns(G, (uint32_t)a)) {
-            h = G.hot[base + a];
-            const uint32_t st = H_STATE(h);
-            want = (st >= RB_INCUBATION && st <= RB_IN_ICU) || (st >= RB_RECOVERED && !(h & H_INCL));
-            if (h & H_QUEUED) h |= H_DET;
-        }
-        list_append(G, c, list, &c->n_list[cur], want, (uint32_t)a, h, lane);
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < G.N; a += gridDim.x * blockDim.x) {
+        if (!owns(G, (uint32_t)a)) continue;
+        uint32_t h = G.hot[base + a];
+        const uint32_t st = H_STATE(h);
+        if (!((st >= RB_INCUBATION && st <= RB_IN_ICU) || (st >= RB_RECOVERED && !(h & H_INCL)))) continue;
+        if (h & H_QUEUED) h |= H_DET;
+        G.perm[base + a] = sweep_slot(G, c, (uint32_t)a);
+        list_add(G, r, c, cur, (uint32_t)a, h);
     }
+}
+// both buffers' segment counters to zero (rb_create, rb_reset, rb_load_state)
+__global__ void k_clear_lists(Eng G) {
+    const size_t n = (size_t)G.R * 2 * G.n_seg;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) G.seg_n[i] = make_uint2(0u, 0u);
 }
 
 #endif

@@ -37,6 +37,6 @@ for cfg in a.configs.split(','):
     if ref is None:
         ref = h
     ctx.close()
-    v = bench.N_AGENTS * a.days * a.replicas / (np.mean(ms) / 1e3)
+    v = bench.N_HUS * a.days * a.replicas / (np.mean(ms) / 1e3)
     print('groups %s wave %s%% %s: %.2f ms/step (min %.2f)  %.3e agent-days/s  rows %s %s'
           % (ng, pct, cfg, np.mean(ms), np.min(ms), v, h, 'OK' if h == ref else 'DIFFER'), flush=True)
