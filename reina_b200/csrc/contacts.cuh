@@ -70,14 +70,13 @@ __device__ __forceinline__ void expose_survivors(const Eng &G, int r, RepCtr *c,
     } else set_problem(cd, RB_OTHER_FAILURE);
 }
 
-__global__ void __launch_bounds__(EX_THREADS, EX_RESIDENT_PER_SM) k_expose(Eng G) {
-    __shared__ int s_place[RB_N_PLACES];
-    __shared__ uint32_t s_ri[EX_WARPS][EX_RCAP], s_rx[EX_WARPS][EX_RCAP];
-    const int r = blockIdx.y + G.r0;
+// The contacts of replica r as seen by ONE CTA: CTA `cta` of the `ncta` that share the replica's work items by grid
+// stride.  s_place: RB_N_PLACES counters of the CTA; ri / rx: this warp's survivor ring.  Called by every thread of the CTA.
+__device__ __forceinline__ void expose_cta(const Eng &G, const int r, const uint32_t cta, const uint32_t ncta, int *s_place, uint32_t *ri, uint32_t *rx) {
     RepCtr *c = &G.ctr[r];
     const DevTable *tb = G.tables[c->epoch];
     const uint32_t n = min(c->n_items, G.cap_items);
-    if (blockIdx.x * blockDim.x >= n) return;
+    if (cta * blockDim.x >= n) return;              // CTA-uniform: nothing for this CTA today
     if (threadIdx.x < RB_N_PLACES) s_place[threadIdx.x] = 0;
     __syncthreads();
     const uint2 *items = G.items + (size_t)r * G.cap_items;
@@ -88,14 +87,13 @@ __global__ void __launch_bounds__(EX_THREADS, EX_RESIDENT_PER_SM) k_expose(Eng G
     const uint32_t *sus = G.sus + (size_t)r * G.sus_words;
     const uint32_t day = (uint32_t)c->day;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *ri = s_ri[warp], *rx = s_rx[warp];
     uint32_t head = 0, tail = 0;
     uint32_t places = 0;                 // this thread's per-place counters, 5 bits each, flushed every 7 iterations
     int since_flush = 0;
-    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t stride = ncta * blockDim.x;
     uint2 nxt = make_uint2(0u, 0u);
-    if (blockIdx.x * blockDim.x + warp * 32 + lane < n) nxt = __ldcs(&items[blockIdx.x * blockDim.x + warp * 32 + lane]);
-    for (uint32_t i0 = blockIdx.x * blockDim.x + warp * 32; i0 < n; i0 += stride) {
+    if (cta * blockDim.x + warp * 32 + lane < n) nxt = __ldcs(&items[cta * blockDim.x + warp * 32 + lane]);
+    for (uint32_t i0 = cta * blockDim.x + warp * 32; i0 < n; i0 += stride) {
         const uint32_t i = i0 + lane;
         const bool valid = i < n;
         const uint2 it = nxt;
@@ -164,25 +162,31 @@ __global__ void __launch_bounds__(EX_THREADS, EX_RESIDENT_PER_SM) k_expose(Eng G
     __syncthreads();
     if (threadIdx.x < RB_N_PLACES && s_place[threadIdx.x]) atomicAdd(&cd->daily_contacts[threadIdx.x], s_place[threadIdx.x]);
 }
+__global__ void __launch_bounds__(EX_THREADS, EX_RESIDENT_PER_SM) k_expose(Eng G) {
+    __shared__ int s_place[RB_N_PLACES];
+    __shared__ uint32_t s_ri[EX_WARPS][EX_RCAP], s_rx[EX_WARPS][EX_RCAP];
+    const int warp = threadIdx.x >> 5;
+    expose_cta(G, blockIdx.y + G.r0, blockIdx.x, gridDim.x, s_place, s_ri[warp], s_rx[warp]);
+}
 
 // ---------------------------------------------------------------- k_resolve
 // DRAIN: this day is followed by the fused day boundary, so tomorrow's test queue -- complete once today's sweep is
 // over -- is drained here by the whole grid instead of by tomorrow's single boundary CTA (HealthcareSystem.iterate,
 // main.pyx:514-545: every queued agent is detected).  The per-age detection counts are parked in drain_det and booked
 // by the boundary at the point where the reference drains, so every stats row is unchanged.
+// Thread `tid` of the `nth` that share replica r's list of successful transmissions.
 template <bool DRAIN>
-__global__ void __launch_bounds__(256, 4) k_resolve(Eng G) {
-    const int r = blockIdx.y + G.r0;
+__device__ __forceinline__ void resolve_part(const Eng &G, const int r, const uint32_t tid, const uint32_t nth) {
     RepCtr *c = &G.ctr[r];
     const size_t base = (size_t)r * G.Npad;
     const uint32_t n = min(c->n_succ, G.cap_succ);
     const Attempt *succ = G.succ + (size_t)r * G.cap_succ;
     // two attempts per thread and pass: their gathers (conflict slot of the target, packed word of the infector) are in
     // flight together.  Two attempts on one target cannot both hold the winning key, so their order does not matter.
-    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t stride = nth;
     const int list = (int)(c->lsel ^ 1u);      // infected during today's sweep: first visited tomorrow, so the entry goes to the lists today's sweep has written
     const bool has_list = c->testing_mode == RB_ALL_WITH_SYMPTOMS_CT;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+    for (uint32_t i = tid; i < n; i += 2 * stride) {
         const uint32_t j = i + stride;
         const bool two = j < n;
         const Attempt a0 = succ[i];
@@ -201,12 +205,12 @@ __global__ void __launch_bounds__(256, 4) k_resolve(Eng G) {
         }
     }
     // verdict for the day boundary that follows: enough capacity events or queued tests to be worth a team of CTAs
-    if (blockIdx.x == 0 && threadIdx.x == 0)
+    if (tid == 0)
         c->wide_day = (c->n_events >= (uint32_t)G.wide_min || c->n_newq >= (uint32_t)G.wide_min) ? 1u : 0u;
     if (DRAIN) {
         const uint32_t nq = min(c->n_newq, G.cap_queue);
         const int32_t *qa = G.q_agent + ((size_t)r * 2 + (c->qsel ^ 1u)) * G.cap_queue;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+        for (uint32_t i = tid; i < nq; i += nth) {
             const int32_t a = qa[i];
             const uint32_t h = G.hot[base + a];
             if (h & H_DET) set_problem(c, RB_WRONG_STATE);   // person_detect, main.pyx:294-298
@@ -214,8 +218,12 @@ __global__ void __launch_bounds__(256, 4) k_resolve(Eng G) {
             mark_detected(G, r, a);
             atomicAdd(&c->drain_det[age_of(G, a)], 1);
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0) c->drained = 1u;
+        if (tid == 0) c->drained = 1u;
     }
+}
+template <bool DRAIN>
+__global__ void __launch_bounds__(256, 4) k_resolve(Eng G) {
+    resolve_part<DRAIN>(G, blockIdx.y + G.r0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 #endif

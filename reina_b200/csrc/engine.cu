@@ -25,6 +25,7 @@
 #include "contacts.cuh"
 #include "shard.cuh"
 #include "setup.cuh"
+#include "run.cuh"
 
 // ================================================================ host side / C-ABI
 static thread_local char g_err[512];
@@ -67,6 +68,7 @@ struct rb_engine {
     // latency-bound phases of one (k_resolve, the single-CTA day boundary) overlap the sweep / contact kernels of another.
     cudaError_t launch_err;             // first failed cooperative launch (launch_boundary)
     int wide_ctas;                      // CTAs per replica of the wide day boundary (<= 1: one CTA per replica)
+    int run_ctas, run_boundary_ctas;    // k_run (few replicas): CTAs per replica of the persistent run kernel (0: not used), of its boundary sub-team
     int n_groups;
     ReplicaGroup grp[MAX_GROUPS];
     cudaEvent_t ev_fork;
@@ -229,6 +231,27 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     const size_t RN = (size_t)R * G.Npad;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     const int sms = prop.multiProcessorCount;
+    // Few replicas: the whole run as one persistent cooperative kernel, a team of co-resident CTAs per replica (run.cuh):
+    // ONE launch per rb_step instead of four per day.  Opt-in (RB_PERSISTENT=1, team size RB_RUN_CTAS): measured on B200 it
+    // does not beat the graph-replayed kernels -- one HUS replica 58.0 us per day with a team of 148 CTAs (62.2 with 64,
+    // 78.6 with 16) against 55.1, 32 replicas 24.4 ms per run against 22.8 -- because a day of few replicas is bound by the
+    // dependent memory round trips INSIDE its phases (lead CTA of one replica: sweep 6.3 + 5.9 us waiting for the slowest
+    // warp, contacts 8.4, resolve 10.7, day boundary 27.6), not by the launches between them.
+    e->run_ctas = 0; e->run_boundary_ctas = 1;
+    {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run, RUN_THREADS, 0));
+        const long long total = (long long)per_sm * sms;
+        bool on = false;
+        if (const char *s = getenv("RB_PERSISTENT")) on = atoi(s) != 0;
+        if (on && total >= 2LL * R) {
+            long long t = total / R; if (t > 64) t = 64;
+            if (const char *s = getenv("RB_RUN_CTAS")) { const int v = atoi(s); if (v >= 1 && (long long)v * R <= total) t = v; }
+            e->run_ctas = (int)t;
+            int b = 1; while (b * 2 <= t && b * 2 <= 16) b *= 2;        // the boundary's team sort wants a power of two
+            e->run_boundary_ctas = b;
+        }
+    }
     {   // Active-list segments (state.cuh, Eng::alist)
         // two per warp of the sweep grid a replica gets in the production geometry (its replica group's share of a wave):
         // a warp streams a segment from end to end, so segments are the unit of load balance -- but every segment costs a
@@ -239,6 +262,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
         long long ctas = (long long)sms * SW_CTAS_PER_SM * (ng > 1 ? pct : 100) / 100 / ((R + ng - 1) / ng);      // as setup_groups sizes the grid
         if (ctas < 1) ctas = 1;
         long long S = 2 * ctas * SW_WARPS, most = (long long)N / 256;
+        if (e->run_ctas) S = 2LL * e->run_ctas * RUN_WARPS;
         if (S > most) S = most;
         G.n_seg = (uint32_t)(S < 1 ? 1 : S);
         G.seg_cap = ((uint32_t)N + G.n_seg - 1) / G.n_seg;        // agents a with a % n_seg == s: never more than this
@@ -299,16 +323,23 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     e->launches += 2;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
-    if (setup_groups(e, sms)) { rb_destroy(e); return 1; }
+    if (e->run_ctas) e->n_groups = 1;
+    else if (setup_groups(e, sms)) { rb_destroy(e); return 1; }
     // wide day boundary: only without replica groups (two wide launches on concurrent streams could each hold half
     // the SMs and wait for the other), one CTA per SM at most
     e->wide_ctas = 1;
     // measured at 5 x 10^7 agents, one replica (ms per 180 days): 1 CTA 80.1; 16 CTAs 50.7; 32: 51.8; 64: 56.7 (the grid
     // barrier grows with the team); threshold 2048 / 8192 / 32768 entries: 47.4 / 56.7 / 59.9
     G.wide_min = 2048;
-    if (e->n_groups == 1 && R * 4 <= sms) { e->wide_ctas = 16; while (e->wide_ctas * R > sms) e->wide_ctas >>= 1; }     // a power of two (team sort)
+    // ... and on one HUS replica (1.7 x 10^6 agents, at most ~3000 events or tests a day) the team only costs: 10.4 ms per
+    // 180 days with it, 9.5 without.  So: populations of 4 x 10^6 agents and more.
+    if (e->n_groups == 1 && R * 4 <= sms && N >= 4000000) { e->wide_ctas = 16; while (e->wide_ctas * R > sms) e->wide_ctas >>= 1; }     // a power of two (team sort)
     if (const char *s = getenv("RB_WIDE_CTAS")) { int v = atoi(s); if (v >= 1 && v <= WIDE_MAX_CTAS && v * R <= sms) e->wide_ctas = v; }
     if (const char *s = getenv("RB_WIDE_MIN")) G.wide_min = atoi(s);     // 0: every day is a wide day (tests)
+    if (const char *s = getenv("RB_WIDE_CTAS")) {      // tests force a boundary team of this size in the persistent kernel too
+        const int v = atoi(s); int b = 1; while (b * 2 <= v && b * 2 <= e->run_ctas) b *= 2;
+        if (e->run_ctas) e->run_boundary_ctas = b;
+    }
     *out = e;
     return 0;
 }
@@ -750,13 +781,27 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     CK(cudaSetDevice(e->cfg.device));
     if (check_days(e, n_days)) return 1;
     if (n_days == 0) return 0;
-    if (!e->sharded && !e->have_graphs && build_graphs(e)) return 1;
+    if (!e->sharded && !e->run_ctas && !e->have_graphs && build_graphs(e)) return 1;
     const Eng &G = e->G;
     const int R = G.R;
     if (e->sharded) {
         CK(cudaEventRecord(e->ev0, e->stream));
         launch_boundary(e, 0, 1, e->stream, G); e->launches++;
         for (int d = 0; d < n_days; d++) if (launch_day_sharded(e, d == n_days - 1)) return 1;
+        CK(cudaEventRecord(e->ev1, e->stream));
+        if (check_launches(e)) return 1;
+        e->day += n_days;
+        return 0;
+    }
+    if (e->run_ctas) {      // few replicas: one persistent cooperative kernel for the whole step
+        CK(cudaEventRecord(e->ev0, e->stream));
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(e->run_ctas, R); cfg.blockDim = dim3(RUN_THREADS); cfg.stream = e->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;      // the teams' barriers need every CTA resident
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_run, G, (int)n_days, e->run_boundary_ctas));
+        e->launches++;
         CK(cudaEventRecord(e->ev1, e->stream));
         if (check_launches(e)) return 1;
         e->day += n_days;

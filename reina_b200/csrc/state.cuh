@@ -129,6 +129,8 @@ struct RepCtr {
     alignas(128) uint32_t n_l0;
     uint32_t n_l1, n_edges;
     // wide day boundary (boundary.cuh, Team): grid barrier word on its own line, today's verdict, per-CTA scan totals
+    alignas(128) unsigned int run_bar;            // k_run: barrier word of the replica's whole team
+    unsigned int run_exit;                        // k_run: CTAs that have left the final barrier
     alignas(128) unsigned int wide_bar;
     alignas(128) uint32_t wide_day;
     int32_t wide_mp[WIDE_MAX_CTAS][4];

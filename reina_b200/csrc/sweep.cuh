@@ -289,23 +289,19 @@ __device__ __forceinline__ void stage_entry(const Eng &G, uint32_t &w, bool &kee
 // One loop per warp over the segments it owns, 32 entries per step, the next step's entries loaded ahead.  Every stage
 // is instantiated exactly ONCE (the heavy stages are thousands of instructions each; a second inlined copy pushes the
 // loop out of the instruction cache).
-__global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
-    __shared__ WarpRings s_rings[SW_WARPS];
-    const int r = blockIdx.y + G.r0;
+// The sweep of replica r as seen by ONE warp: warp `first` of the `n_warps` that share the replica's segments.
+__device__ __forceinline__ void sweep_warp(const Eng &G, const int r, const uint32_t first, const uint32_t n_warps, WarpRings &W, const int lane) {
     RepCtr *c = &G.ctr[r];
     const DevTable *tb = G.tables[c->epoch];
     uint2 *items = G.items + (size_t)r * G.cap_items;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpRings &W = s_rings[warp];
     RepCtr *cd = !G.xbuf ? c : xslot_of(G, G.rank, c->day).hdr;      // counters the sweep adds to
     const uint32_t cur = c->lsel;
-    const uint32_t n_warps = gridDim.x * SW_WARPS;
     uint32_t e_head = 0, e_tail = 0, t_head = 0, t_tail = 0;
 
     // One pass per owned segment plus a final pass that only drains the rings: the stages have exactly one call site each.
     uint2 cnt_next = make_uint2(0u, 0u);      // the counters of the next segment are fetched while this one is processed
-    if (blockIdx.x * SW_WARPS + warp < G.n_seg) cnt_next = *seg_count(G, r, cur, blockIdx.x * SW_WARPS + warp);
-    for (uint32_t seg = blockIdx.x * SW_WARPS + warp; ; seg += n_warps) {
+    if (first < G.n_seg) cnt_next = *seg_count(G, r, cur, first);
+    for (uint32_t seg = first; ; seg += n_warps) {
         const bool tail = seg >= G.n_seg;
         const uint2 cnt = cnt_next;
         cnt_next = make_uint2(0u, 0u);
@@ -344,6 +340,11 @@ __global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
         if (tail) break;
         if (lane == 0) seg_count(G, r, cur ^ 1u, seg)->x = out_n;     // front of tomorrow's segment; its back fills by atomics
     }
+}
+__global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) k_sweep(Eng G) {
+    __shared__ WarpRings s_rings[SW_WARPS];
+    const int warp = threadIdx.x >> 5;
+    sweep_warp(G, blockIdx.y + G.r0, blockIdx.x * SW_WARPS + warp, gridDim.x * SW_WARPS, s_rings[warp], threadIdx.x & 31);
 }
 
 // ---------------------------------------------------------------- list maintenance (not on the per-day path)
