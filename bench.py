@@ -37,6 +37,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries the ONE JSON line: whatever NCCL has to say (its version banner, NCCL_DEBUG=INFO output) goes to stderr
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
 N_HUS = 1685983
 N_SYNTH = 50_000_000

@@ -2,19 +2,22 @@
 // calls) as hand-written CUDA for sm_100a, behind the C-ABI of include/reina_b200.h.
 //
 //   state.cuh     data layout in HBM (agents stored AGE-SORTED, so age is implied by position and a contact target is
-//                 age_start[band] + u32 % band_size with no indirection), per-replica counters, shared device helpers
+//                 age_start[band] + u32 % band_size with no indirection), the segmented active lists, per-replica
+//                 counters, shared device helpers, person_infect
 //   boundary.cuh  k_pre / k_post / k_between, one CTA per replica or (few replicas of a large population) a team of
 //                 co-resident CTAs with a grid barrier: stats row, intervention deltas, imports, test queue + contact
 //                 tracing, vaccination, sweep start; beds / ICU first-come-first-served = sort by sweep position +
 //                 max-plus scan
-//   sweep.cuh     k_sweep: Context._iterate_people / person_advance over the active agents; emits contact work items,
-//                 capacity events and test-queue entries tagged with sweep position
-//   contacts.cuh  k_expose: one thread per group of four sampled contacts (row search, target gather, transmission draw,
-//                 atomicMin(winner[target], sweep position of infector | slot)); k_resolve: winners become infected
+//   sweep.cuh     k_sweep: Context._iterate_people / person_advance over the dense active lists (a warp owns whole
+//                 segments); emits contact work items, capacity events and test-queue entries tagged with sweep position
+//   contacts.cuh  k_expose: one thread per group of four sampled contacts (O(1) row pick, target gather, transmission
+//                 draw, atomicMin(winner[target], sweep position of infector | slot)); k_resolve: winners become infected
+//   run.cuh       k_run: opt-in persistent cooperative kernel, the whole run of a few replicas in one launch
 //   shard.cuh     population-sharded mode: k_publish / k_wait (per-day flags in NVLink peer memory) and k_merge, which
 //                 pulls and applies every rank's message of the day
-//   setup.cuh     set_initial_state, initialisation, snapshot, ensemble moments, samplers
-//   this file     host side: engine handle, launch geometry, CUDA graphs, NCCL binding, the extern "C" entry points
+//   setup.cuh     set_initial_state, initialisation, contact-row guide, snapshot, ensemble moments, samplers
+//   this file     host side: engine handle, launch geometry, replica groups, CUDA graphs, NCCL binding (ensemble reduce,
+//                 sharded mode), the extern "C" entry points
 //
 // Per day and replica group (reference order, main.pyx:1994-2016): k_sweep -> k_expose -> k_resolve -> k_between.  Every order-dependent
 // step of the sequential reference is resolved through the agent's sweep position, so the result is bit-identical to the

@@ -28,20 +28,16 @@ union RunSmem {
     SmemSmall bd;
 };
 
-// kind: 0 = start of the first day (k_pre), 1 = end of the last day (k_post), 2 = end of a day + start of the next (k_between)
+// kind: 0 = start of the first day (k_pre), 1 = end of the last day (k_post), 2 = end of a day + start of the next (k_between).
+// ONE call site of post_body / pre_body each (they are thousands of instructions): the team that runs them is picked first.
 __device__ __forceinline__ void run_boundary(const Eng &G, const int r, RepCtr *c, RunSmem &S, Team &T, Team &B, const int kind) {
     const bool wide = B.ncta > 1 && (kind == 0 ? c->n_queue >= (uint32_t)G.wide_min : c->wide_day != 0u);
-    if (wide) {
-        if (blockIdx.x < B.ncta) {
-            if (kind != 0) post_body(G, r, S.bd, B);
-            if (kind == 2) team_sync(B);
-            if (kind != 1) pre_body(G, r, S.bd, B);
-        }
-    } else if (blockIdx.x == 0) {
-        Team L = team_of(c, 0, 1);
-        if (kind != 0) post_body(G, r, S.bd, L);
-        if (kind == 2) __syncthreads();
-        if (kind != 1) pre_body(G, r, S.bd, L);
+    Team L = team_of(c, 0, 1);
+    Team &X = wide ? B : L;
+    if (wide ? blockIdx.x < B.ncta : blockIdx.x == 0) {
+        if (kind != 0) post_body(G, r, S.bd, X);
+        if (kind == 2) team_sync(X);
+        if (kind != 1) pre_body(G, r, S.bd, X);
     }
     team_sync(T);
 }
@@ -59,23 +55,23 @@ __global__ void __launch_bounds__(RUN_THREADS, RUN_CTAS_PER_SM) k_run(Eng G, int
     long long t0 = 0;
     auto lap = [&](int k) { if (timing) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); if (k >= 0) c->dbg_t[8 + k] += t - t0; t0 = t; } };
     lap(-1);
-    run_boundary(G, r, c, S, T, B, 0);
-    lap(0);
-    for (int d = 0; d < n_days; d++) {
+    for (int d = -1; d < n_days; d++) {       // d = -1: only the start of the first day
         const bool last = d == n_days - 1;
-        sweep_warp(G, r, blockIdx.x * RUN_WARPS + warp, gridDim.x * RUN_WARPS, S.rings[warp], lane);
-        lap(1);
-        team_sync(T);
-        lap(2);
-        expose_cta(G, r, blockIdx.x, gridDim.x, S.ex.place, S.ex.ri[warp], S.ex.rx[warp]);
-        team_sync(T);
-        lap(3);
-        if (last) resolve_part<false>(G, r, blockIdx.x * RUN_THREADS + threadIdx.x, gridDim.x * RUN_THREADS);
-        else resolve_part<true>(G, r, blockIdx.x * RUN_THREADS + threadIdx.x, gridDim.x * RUN_THREADS);
-        team_sync(T);
-        lap(4);
-        run_boundary(G, r, c, S, T, B, last ? 1 : 2);
-        lap(5);
+        if (d >= 0) {
+            sweep_warp(G, r, blockIdx.x * RUN_WARPS + warp, gridDim.x * RUN_WARPS, S.rings[warp], lane);
+            lap(1);
+            team_sync(T);
+            lap(2);
+            expose_cta(G, r, blockIdx.x, gridDim.x, S.ex.place, S.ex.ri[warp], S.ex.rx[warp]);
+            team_sync(T);
+            lap(3);
+            if (last) resolve_part<false>(G, r, blockIdx.x * RUN_THREADS + threadIdx.x, gridDim.x * RUN_THREADS);
+            else resolve_part<true>(G, r, blockIdx.x * RUN_THREADS + threadIdx.x, gridDim.x * RUN_THREADS);
+            team_sync(T);
+            lap(4);
+        }
+        run_boundary(G, r, c, S, T, B, d < 0 ? 0 : (last ? 1 : 2));
+        lap(d < 0 ? 0 : 5);
     }
     // Both barrier words back to zero for the next launch -- by the LAST CTA to leave: a CTA counts itself out only after
     // its own wait on the final barrier is over, so when the count is complete nobody polls the words any more.

@@ -20,13 +20,14 @@
 //
 // Work flows through two warp-private shared-memory rings, each drained only in full batches of 32, so the two heavy
 // stages execute on dense warps and no block-level barrier exists anywhere:
-//   stage 1 (every entry)     day counters, is the agent infectious today, is anything else due; survivors -> next list
+//   stage 1 (every entry)     day counters, is the agent infectious today, is anything else due; survivors -> front of
+//                             tomorrow's segment
 //   ring E (infectious)    -> stage E: number of contacts (one Philox block + tabulated distribution), contact work
-//                             items allocated with a warp prefix sum + one atomic and written coalesced
+//                             items reserved with one scan + one atomic per batch
 //   ring T (something due) -> stage T: everything that needs the authoritative word or the agent record: state changes
 //                             (symptom onset with its gamma draw, end of illness, ward / ICU exits -> capacity events
 //                             tagged with the sweep position), pending bed / ICU claims decided by the day boundary,
-//                             R bookkeeping of removed agents
+//                             R bookkeeping of removed agents; what stays listed -> back of tomorrow's segment
 #ifndef SW_THREADS
 #define SW_THREADS 128
 #endif

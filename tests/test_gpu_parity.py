@@ -246,7 +246,9 @@ def test_persistent_run_kernel(cuda_lib, oracle_lib, monkeypatch, wide):
     gpu, cpu = _pair(cuda_lib, oracle_lib, seed=11, **kw)
     launches0 = gpu._engine.launch_count()
     _run_and_compare(gpu, cpu, 120, chunk=40)
-    assert gpu._engine.launch_count() - launches0 <= 3 + 3      # one k_run per chunk (+ the list flushes of read_agents)
+    # one k_run per chunk, plus a guide build per mobility epoch met while planning and the list flushes of read_agents;
+    # the per-phase kernels would have taken 1 + 4 x 120 launches
+    assert gpu._engine.launch_count() - launches0 <= 3 + 16
     ens = helpers.make_context(cuda_lib, seed=40, n_replicas=3, **kw)
     ens.run(100)
     rows = ens.series(0, 100)
