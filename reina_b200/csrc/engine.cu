@@ -50,6 +50,7 @@ struct rb_engine {
     cudaEvent_t ev0, ev1;
     std::vector<void *> allocs;
     std::vector<DevTable *> tables;     // host copy of the device pointer table
+    std::vector<std::vector<uint8_t>> table_args, table_host;      // per epoch: the arguments last seen, the host-built part of the DevTable
     DevTable **d_tables;
     int n_table_slots;
     rb_day_params *d_sched;
@@ -129,24 +130,17 @@ static uint32_t pow2_at_least(uint64_t x) { uint32_t p = 1024; while (p < x) p <
 
 extern "C" const char *rb_last_error(void) { return g_err; }
 
-static int init_counters(rb_engine *e, uint32_t seed) {
-    const rb_config *cfg = &e->cfg;
-    const int R = cfg->n_replicas;
-    std::vector<RepCtr> hc(R);
-    memset(hc.data(), 0, sizeof(RepCtr) * R);
-    for (int r = 0; r < R; r++) {
-        RepCtr &c = hc[r];
-        for (int a = 0; a < cfg->n_ages; a++) c.counts[RB_A_SUSCEPTIBLE][a] = e->age_counts[a];
-        c.beds = c.avail_beds = cfg->hospital_beds; c.icu = c.avail_icu = cfg->icu_units;
-        c.p_successful_tracing = 1.0f;
-        c.seed = seed + (uint32_t)r;
-        u32x4 k = philox(c.seed, 0, 0, PU_PERM, 0);
-        c.fkey[0] = k.x; c.fkey[1] = k.y; c.fkey[2] = k.z; c.fkey[3] = k.w;
-        for (int i = 0; i < RB_MAX_VACC; i++) c.vacc_cursor[i] = -2;
-    }
-    CK(cudaMemcpyAsync(e->G.ctr, hc.data(), sizeof(RepCtr) * R, cudaMemcpyHostToDevice, e->stream));
-    e->h2d_bytes += (int64_t)sizeof(RepCtr) * R;
-    CK(cudaStreamSynchronize(e->stream));
+// A fresh population on the device: counters, packed words, agent records, bitmaps, empty active lists.  `sparse`: the
+// arrays hold the end of a previous run (k_init).
+static int init_population(rb_engine *e, uint32_t seed, bool sparse) {
+    const Eng &G = e->G;
+    k_init_counters<<<G.R, 128, 0, e->stream>>>(G, seed, e->cfg.hospital_beds, e->cfg.icu_units);
+    if (sparse) k_init<true><<<dim3(e->sweep_blocks, G.R), 256, 0, e->stream>>>(G);
+    else k_init<false><<<dim3(e->sweep_blocks, G.R), 256, 0, e->stream>>>(G);
+    k_init_bitmaps<<<dim3(8, G.R), 256, 0, e->stream>>>(G);
+    k_clear_lists<<<128, 256, 0, e->stream>>>(G);
+    e->launches += 4;
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -308,7 +302,6 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     CK(cudaMemcpy(d_icum, import_cum, sizeof(float) * cfg->n_import_classes, cudaMemcpyHostToDevice));
     G.age_blk = d_ab; G.variants = dv; G.age_start = d_as; G.group_of_age = d_ga; G.import_lo = d_ilo; G.import_hi = d_ihi; G.import_cum = d_icum;
     e->age_counts.assign(age_counts, age_counts + cfg->n_ages);
-    if (init_counters(e, cfg->seed)) { rb_destroy(e); return 1; }
     CK(cudaMemset(G.stats, 0, sizeof(int32_t) * (size_t)R * (cfg->max_days + 1) * G.row_len));
     CK(cudaMemset(e->d_sched, 0, sizeof(rb_day_params) * ((size_t)cfg->max_days + 1)));
     // launch geometry: grid-stride kernels sized in multiples of the SM count
@@ -321,10 +314,7 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     e->list_blocks = sms * EX_CTAS_PER_SM / R; if (e->list_blocks < 2) e->list_blocks = 2;
     // k_resolve is a chain of dependent scattered accesses per infection: enough threads for one pass over the day's list
     e->resolve_blocks = resolve_grid(G.N, sms, 100, R);
-    k_init<<<dim3(e->sweep_blocks, R), 256, 0, e->stream>>>(G);
-    k_clear_lists<<<sms, 256, 0, e->stream>>>(G);
-    e->launches += 2;
-    CK(cudaGetLastError());
+    if (init_population(e, cfg->seed, false)) { rb_destroy(e); return 1; }
     CK(cudaStreamSynchronize(e->stream));
     if (e->run_ctas) e->n_groups = 1;
     else if (setup_groups(e, sms)) { rb_destroy(e); return 1; }
@@ -390,10 +380,7 @@ extern "C" int rb_reset(rb_engine *e, uint32_t seed) {
     e->cfg.seed = seed;
     e->day = 0;
     e->G.xepoch++;
-    if (init_counters(e, seed)) return 1;
-    k_init<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G);
-    k_clear_lists<<<128, 256, 0, e->stream>>>(e->G);
-    e->launches += 2;
+    if (init_population(e, seed, true)) return 1;
     if (e->has_ipc) {
         k_initial_state<<<e->G.R, 32, 0, e->stream>>>(e->G, e->ipc);
         k_rebuild_lists<<<dim3(e->sweep_blocks, e->G.R), 256, 0, e->stream>>>(e->G);
@@ -456,6 +443,21 @@ extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *
     }
     DevTable *h; int slot;
     if (stage_slot(e, &h, &slot)) return 1;
+    // The same table is usually sent again for every new batch of seeds (Context.upload_inputs): the inputs are copied to
+    // the device every time, but the derived part (integer thresholds, band offsets, guides) is only recomputed when the
+    // arguments differ from what this epoch was last set to.
+    const size_t nA = (size_t)e->cfg.n_ages, nAR = nA * RB_MAX_ROWS;
+    const void *arg[8] = {n_rows, cum_p, age_lo, age_hi, place, mask_p, nr_contacts, ncontact_cdf};
+    const size_t len[8] = {nA * 4, nAR * 8, nAR * 4, nAR * 4, nAR, nAR * 4, nA * 8, nA * 2 * RB_NCDF * 8};
+    size_t total = 0; for (int i = 0; i < 8; i++) total += len[i];
+    if ((size_t)epoch >= e->table_args.size()) { e->table_args.resize(epoch + 1); e->table_host.resize(epoch + 1); }
+    std::vector<uint8_t> &seen = e->table_args[epoch], &built = e->table_host[epoch];
+    bool same = seen.size() == total && built.size() == TABLE_HOST_BYTES;
+    for (size_t i = 0, off = 0; i < 8 && same; off += len[i], i++) same = memcmp(seen.data() + off, arg[i], len[i]) == 0;
+    if (same) memcpy(h, built.data(), TABLE_HOST_BYTES);
+    else {
+    seen.resize(total);
+    for (size_t i = 0, off = 0; i < 8; off += len[i], i++) memcpy(seen.data() + off, arg[i], len[i]);
     memset(h, 0, TABLE_HOST_BYTES);
     for (int age = 0; age < e->cfg.n_ages; age++) {
         h->n_rows[age] = n_rows[age];
@@ -490,6 +492,8 @@ extern "C" int rb_set_contact_table(rb_engine *e, int32_t epoch, const int32_t *
                 const bool exact = k >= limit || h->ncdf[age][cls][k] >= (double)(b + 1) / 256.0;
                 h->nguide[age][cls][b] = (uint8_t)(k | (exact ? 0 : 128));
             }
+    built.assign((const uint8_t *)h, (const uint8_t *)h + TABLE_HOST_BYTES);
+    }
     DevTable *d = e->tables[epoch];
     if (!d) {
         if (dalloc(e, &d, 1)) return 1;
@@ -514,13 +518,24 @@ extern "C" int rb_set_schedule(rb_engine *e, int32_t day0, int32_t n, const rb_d
     return 0;
 }
 
+// Launch of a per-day kernel.  (Programmatic dependent launch -- cudaLaunchAttributeProgrammaticStreamSerialization with a
+// griddepcontrol.wait at the head of every kernel, captured into the graphs as programmatic edges -- was built and
+// measured here: bit-exact, but no gain over plain graph edges for one replica (52.5 vs 50.7 us per day) and a loss for
+// ensembles (256 replicas 116.9 vs 104.2 ms: the early-scheduled CTAs of a group's next kernel hold SM slots that another
+// group's running kernel could use).  Removed again.)
+template <typename K>
+static void launch_k(rb_engine *e, K kernel, dim3 grid, int threads, cudaStream_t st, const Eng &G) {
+    (void)e;
+    kernel<<<grid, threads, 0, st>>>(G);
+}
+
 // The day boundary: one CTA per replica, or -- few replicas of a large population -- a cooperative launch of
 // wide_ctas co-resident CTAs per replica (boundary.cuh, Team).  kind: 0 = k_pre, 1 = k_post, 2 = k_between.
 static void launch_boundary(rb_engine *e, int kind, int R, cudaStream_t st, const Eng &G) {
     if (e->wide_ctas <= 1) {
-        if (kind == 0) k_pre<false><<<R, PRE_THREADS, 0, st>>>(G);
-        else if (kind == 1) k_post<false><<<R, PRE_THREADS, 0, st>>>(G);
-        else k_between<false><<<R, PRE_THREADS, 0, st>>>(G);
+        if (kind == 0) launch_k(e, k_pre<false>, dim3(R), PRE_THREADS, st, G);
+        else if (kind == 1) launch_k(e, k_post<false>, dim3(R), PRE_THREADS, st, G);
+        else launch_k(e, k_between<false>, dim3(R), PRE_THREADS, st, G);
         return;
     }
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
@@ -538,9 +553,9 @@ static void launch_boundary(rb_engine *e, int kind, int R, cudaStream_t st, cons
 // One "segment" = the grid kernels of day d followed by the fused day boundary d -> d+1.
 static void launch_segment(rb_engine *e, cudaStream_t st) {
     const Eng &G = e->G;
-    k_sweep<<<dim3(e->sweep_blocks, G.R), SW_THREADS, 0, st>>>(G);
-    k_expose<<<dim3(e->list_blocks, G.R), EX_THREADS, 0, st>>>(G);
-    k_resolve<true><<<dim3(e->resolve_blocks, G.R), 256, 0, st>>>(G);
+    launch_k(e, k_sweep, dim3(e->sweep_blocks, G.R), SW_THREADS, st, G);
+    launch_k(e, k_expose, dim3(e->list_blocks, G.R), EX_THREADS, st, G);
+    launch_k(e, k_resolve<true>, dim3(e->resolve_blocks, G.R), 256, st, G);
     launch_boundary(e, 2, G.R, st, G);
 }
 
@@ -548,10 +563,10 @@ static void launch_segment(rb_engine *e, cudaStream_t st) {
 // device memory), so a captured graph of GRAPH_DAYS segments is replayed for any stretch of days.
 static void launch_group_segment(rb_engine *e, const ReplicaGroup &q, bool stagger_mark) {
     Eng G = e->G; G.r0 = q.r0;
-    k_sweep<<<dim3(q.sweep_blocks, q.R), SW_THREADS, 0, q.stream>>>(G);
-    k_expose<<<dim3(q.list_blocks, q.R), EX_THREADS, 0, q.stream>>>(G);
+    launch_k(e, k_sweep, dim3(q.sweep_blocks, q.R), SW_THREADS, q.stream, G);
+    launch_k(e, k_expose, dim3(q.list_blocks, q.R), EX_THREADS, q.stream, G);
     if (stagger_mark) cudaEventRecord(q.ev_stagger, q.stream);       // the next group starts its day here
-    k_resolve<true><<<dim3(q.resolve_blocks, q.R), 256, 0, q.stream>>>(G);
+    launch_k(e, k_resolve<true>, dim3(q.resolve_blocks, q.R), 256, q.stream, G);
     launch_boundary(e, 2, q.R, q.stream, G);
 }
 
@@ -823,9 +838,9 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
             while (mid >= GRAPH_DAYS) { CK(cudaGraphLaunch(q.graph[0], q.stream)); mid -= GRAPH_DAYS; e->launches += 4 * GRAPH_DAYS; }
             while (mid > 0) { CK(cudaGraphLaunch(q.graph[1], q.stream)); mid -= 1; e->launches += 4; }
             Eng Gq = G; Gq.r0 = q.r0;
-            k_sweep<<<dim3(q.sweep_blocks, q.R), SW_THREADS, 0, q.stream>>>(Gq);
-            k_expose<<<dim3(q.list_blocks, q.R), EX_THREADS, 0, q.stream>>>(Gq);
-            k_resolve<false><<<dim3(q.resolve_blocks, q.R), 256, 0, q.stream>>>(Gq);
+            launch_k(e, k_sweep, dim3(q.sweep_blocks, q.R), SW_THREADS, q.stream, Gq);
+            launch_k(e, k_expose, dim3(q.list_blocks, q.R), EX_THREADS, q.stream, Gq);
+            launch_k(e, k_resolve<false>, dim3(q.resolve_blocks, q.R), 256, q.stream, Gq);
             launch_boundary(e, 1, q.R, q.stream, Gq);
             e->launches += 4;
             CK(cudaEventRecord(q.ev_join, q.stream));
@@ -841,9 +856,9 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     int mid = n_days - 1;
     while (mid >= GRAPH_DAYS) { CK(cudaGraphLaunch(e->graph[0], e->stream)); mid -= GRAPH_DAYS; e->launches += 4 * GRAPH_DAYS; }
     while (mid > 0) { CK(cudaGraphLaunch(e->graph[1], e->stream)); mid -= 1; e->launches += 4; }
-    k_sweep<<<dim3(e->sweep_blocks, R), SW_THREADS, 0, e->stream>>>(G);
-    k_expose<<<dim3(e->list_blocks, R), EX_THREADS, 0, e->stream>>>(G);
-    k_resolve<false><<<dim3(e->resolve_blocks, R), 256, 0, e->stream>>>(G);
+    launch_k(e, k_sweep, dim3(e->sweep_blocks, R), SW_THREADS, e->stream, G);
+    launch_k(e, k_expose, dim3(e->list_blocks, R), EX_THREADS, e->stream, G);
+    launch_k(e, k_resolve<false>, dim3(e->resolve_blocks, R), 256, e->stream, G);
     launch_boundary(e, 1, R, e->stream, G);
     e->launches += 4;
     CK(cudaEventRecord(e->ev1, e->stream));

@@ -122,15 +122,45 @@ __global__ void k_build_guide(DevTable *tb, int n_ages) {
 }
 
 // ---------------------------------------------------------------- misc kernels
+// The per-replica counters of a fresh Context (Context.__init__, main.pyx:1759-1781): everything zero, every age
+// susceptible, full capacity, the replica's seed and the keys of its sweep-order permutation.  One CTA per replica.
+__global__ void k_init_counters(Eng G, uint32_t seed, int32_t beds, int32_t icu) {
+    RepCtr *c = &G.ctr[blockIdx.x];
+    uint32_t *w = reinterpret_cast<uint32_t *>(c);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)(sizeof(RepCtr) / 4); i += blockDim.x) w[i] = 0u;
+    __syncthreads();
+    for (int age = threadIdx.x; age < G.n_ages; age += blockDim.x) c->counts[RB_A_SUSCEPTIBLE][age] = G.age_start[age + 1] - G.age_start[age];
+    if (threadIdx.x == 0) {
+        c->beds = c->avail_beds = beds; c->icu = c->avail_icu = icu;
+        c->p_successful_tracing = 1.0f;
+        c->seed = seed + blockIdx.x;
+        const u32x4 k = philox(c->seed, 0, 0, PU_PERM, 0);
+        c->fkey[0] = k.x; c->fkey[1] = k.y; c->fkey[2] = k.z; c->fkey[3] = k.w;
+        for (int i = 0; i < RB_MAX_VACC; i++) c->vacc_cursor[i] = -2;
+    }
+}
+
+// Every agent SUSCEPTIBLE and untouched.  SPARSE (rb_reset): the arrays hold the end of a previous run, in which an agent
+// was only ever written if it stopped being susceptible or its packed word became non-zero (vaccinated, queued,
+// detected) -- conflict slots are always handed back idle -- so only those agents are rewritten: the reset reads 4 bytes
+// per agent and writes 36 for the ~20 % a HUS run has touched, instead of writing 36 for everybody.
+template <bool SPARSE>
 __global__ void k_init(Eng G) {
     const int r = blockIdx.y;
     const size_t base = (size_t)r * G.Npad;
+    const uint32_t *sus = G.sus + (size_t)r * G.sus_words;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < G.Npad; i += gridDim.x * blockDim.x) {
-        // padding words beyond N are marked RECOVERED+included so that the sweep skips them
-        G.hot[base + i] = i < G.N ? 0u : (RB_RECOVERED | H_INCL);
+        // padding words beyond N are marked RECOVERED+included (nobody ever lists them)
+        const uint32_t fresh = i < G.N ? 0u : (RB_RECOVERED | H_INCL);
+        if (SPARSE && i < G.N && G.hot[base + i] == 0u && ((sus[i >> 5] >> (i & 31)) & 1u)) continue;
+        G.hot[base + i] = fresh;
         AgentRec z; z.winner = KEY_IDLE; z.infector = -1; z.first_child = -1; z.next_sib = -1; z.inf_key = 0; z.cold = 0; z.vacc_day = -1; z.pad = 0;
         G.rec[base + i] = z;
     }
+}
+// the two bitmaps of a fresh population; after k_init<true>, which still reads the old susceptibility bits
+__global__ void k_init_bitmaps(Eng G) {
+    const int r = blockIdx.y;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < G.sus_words; w += gridDim.x * blockDim.x) {
         int first = w * 32;
         uint32_t m = first + 32 <= G.N ? 0xffffffffu : (first >= G.N ? 0u : ((1u << (G.N - first)) - 1u));
