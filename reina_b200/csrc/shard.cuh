@@ -94,24 +94,14 @@ __global__ void __launch_bounds__(256) k_merge(Eng G) {
         }
     }
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    // per-age counter deltas of the sweeps: the loads from all ranks are issued TOGETHER (one NVLink round trip, not one
-    // per rank: with a loop over the ranks every add waits for its own load, 8 ranks = 8 round trips in sequence)
-    for (uint32_t i = gtid; i < RB_N_ATTRS * RB_MAX_AGES; i += gsz) {
-        int v[MAX_RANKS];
-#pragma unroll
-        for (int k = 0; k < MAX_RANKS; k++) v[k] = k < nrk ? pull(&xslot_of(G, k, day).hdr->counts[0][0] + i) : 0;
+    for (uint32_t i = gtid; i < RB_N_ATTRS * RB_MAX_AGES; i += gsz) {      // per-age counter deltas of the sweeps
         int d = 0;
-#pragma unroll
-        for (int k = 0; k < MAX_RANKS; k++) d += v[k];
+        for (int k = 0; k < nrk; k++) d += pull(&xslot_of(G, k, day).hdr->counts[0][0] + i);
         if (d) (&c->counts[0][0])[i] += d;
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x < RB_N_PLACES) {
-        int v[MAX_RANKS];
-#pragma unroll
-        for (int k = 0; k < MAX_RANKS; k++) v[k] = k < nrk ? pull(&xslot_of(G, k, day).hdr->daily_contacts[threadIdx.x]) : 0;
         int d = 0;
-#pragma unroll
-        for (int k = 0; k < MAX_RANKS; k++) d += v[k];
+        for (int k = 0; k < nrk; k++) d += pull(&xslot_of(G, k, day).hdr->daily_contacts[threadIdx.x]);
         c->daily_contacts[threadIdx.x] += d;
     }
     if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64) {        // one warp: lane k reads rank k's scalars
