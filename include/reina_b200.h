@@ -232,6 +232,12 @@ int rb_reduce_moments(rb_engine *e, int32_t day0, int32_t n, double *sum, double
  * libnccl.so.2 is loaded at run time by these calls only. */
 int rb_shard_unique_id(uint8_t *out128);
 int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const uint8_t *unique_id128, float exchange_capacity);
+/* The same join for `nranks` engines of ONE process (rank k = engines[k]): no NCCL and no CUDA IPC, every rank reads the
+ * others' message buffers through plain device pointers (engines on one device, or on devices with peer access, which
+ * this call enables).  Each engine must then be stepped from its own host thread (a rank's day ends only after every
+ * rank's sweep of that day has been launched), and all of them must be idle before any one is destroyed.  This is how a
+ * single-GPU box exercises the multi-rank exchange: several ranks, each on its own stream of the one device. */
+int rb_shard_init_local(rb_engine **engines, int32_t nranks, float exchange_capacity);
 int32_t rb_shard_rank(rb_engine *e);
 int32_t rb_shard_nranks(rb_engine *e);
 int64_t rb_shard_message_bytes(rb_engine *e);   /* capacity of one rank's daily message (what the all-gather path moves) */

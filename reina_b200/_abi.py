@@ -88,7 +88,7 @@ SYMBOLS = ['create', 'destroy', 'reset', 'set_initial_state', 'step_profiled', '
 
 
 # population-sharded mode: exported by the CUDA library only (the sequential CPU oracle has no ranks)
-SHARD_SYMBOLS = ['shard_unique_id', 'shard_init', 'shard_rank', 'shard_nranks', 'shard_message_bytes', 'shard_exchange',
+SHARD_SYMBOLS = ['shard_unique_id', 'shard_init', 'shard_init_local', 'shard_rank', 'shard_nranks', 'shard_message_bytes', 'shard_exchange',
                  # checkpoint / resume of the device-resident state
                  'state_bytes', 'save_state', 'load_state',
                  # ensemble communicator (NCCL), production-geometry timing, measurement aids
@@ -163,6 +163,7 @@ class Library:
                 f[name] = getattr(self.dll, prefix + name)
             f['shard_unique_id'].argtypes = [C.c_char_p]
             f['shard_init'].argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_float]
+            f['shard_init_local'].argtypes = [C.POINTER(vp), C.c_int32, C.c_float]
             f['shard_rank'].argtypes = [vp]
             f['shard_nranks'].argtypes = [vp]
             f['shard_message_bytes'].argtypes = [vp]
@@ -380,6 +381,16 @@ class Engine:
         """(host -> device, device -> host) bytes copied by this handle so far."""
         f = self.lib.f['copied_bytes']
         return int(f(self.h, 0)), int(f(self.h, 1))
+
+
+def shard_init_local(engines, exchange_capacity=0.0):
+    """Join the Engine objects of THIS process into one population-sharded simulation: rank k = engines[k]
+    (rb_shard_init_local: plain device pointers instead of NCCL + CUDA IPC).  Step each from its own thread."""
+    lib = engines[0].lib
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    lib.check(lib.f['shard_init_local'](arr, len(engines), exchange_capacity), 'shard_init_local')
+    for k, e in enumerate(engines):
+        e.rank, e.nranks = k, len(engines)
 
 
 def shard_unique_id(lib=None):

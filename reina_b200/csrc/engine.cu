@@ -82,6 +82,9 @@ struct rb_engine {
     bool shard_timing; std::vector<cudaEvent_t> shard_events;
     int n_peer_open;                    // peer buffers mapped through CUDA IPC: ranks [0, n_peer_open) except the own one
     int merge_blocks;
+    int prio, prio_high;                // RB_PRIO: launch the latency-bound kernels with the device's highest priority
+    uint32_t xepoch; uint32_t *d_xepoch;   // host copy / device word of Eng::xepoch
+    cudaGraphExec_t sh_graph[2]; bool have_sh_graphs;      // population-sharded days (peer-memory exchange): 16 days / 1 day
     Ipc ipc; bool has_ipc;              // initial population condition, re-applied by rb_reset
 };
 
@@ -171,6 +174,7 @@ extern "C" void rb_destroy(rb_engine *e) {
         cudaStreamDestroy(e->grp[g].stream); cudaEventDestroy(e->grp[g].ev_stagger); cudaEventDestroy(e->grp[g].ev_join);
     }
     if (e->n_groups > 1) cudaEventDestroy(e->ev_fork);
+    if (e->have_sh_graphs) { cudaGraphExecDestroy(e->sh_graph[0]); cudaGraphExecDestroy(e->sh_graph[1]); }
     for (int k = 0; k < e->n_peer_open; k++) if (k != e->G.rank && e->G.xpeer[k]) cudaIpcCloseMemHandle(e->G.xpeer[k]);
     if (e->comm) g_nccl.CommDestroy(e->comm);
     for (void *p : e->allocs) cudaFree(p);
@@ -196,6 +200,8 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
     rb_engine *e = new rb_engine();
     e->cfg = *cfg; e->day = 0; e->last_ms = 0; e->launches = 0; e->h2d_bytes = 0; e->d2h_bytes = 0; e->have_graphs = false; e->comm = nullptr; e->comm_rank = 0; e->comm_size = 1; e->sharded = false; e->merge_blocks = 1;
     e->has_ipc = false; e->h_stage = nullptr; e->n_stage = 0; e->n_groups = 1; e->wide_ctas = 1; e->n_peer_open = 0; e->launch_err = cudaSuccess; e->shard_timing = getenv("RB_SHARD_TIMING") != nullptr;
+    e->xepoch = 0; e->d_xepoch = nullptr; e->have_sh_graphs = false;
+    { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); e->prio_high = hi; e->prio = (cfg->n_replicas >= 32 && cfg->n_replicas < 128) ? 1 : 0; if (const char *s = getenv("RB_PRIO")) e->prio = atoi(s); }
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     Eng &G = e->G;
@@ -341,8 +347,11 @@ extern "C" int rb_create(const rb_config *cfg, const int32_t *age_counts, const 
 // with full-wave grids 154.9; 3 x 100 % 152.6; 4 x 50 % 153.0; 4 x 100 % 152.2; 8 x 50 % 156.0 -- the grids are
 // oversubscribed on purpose, a group in its latency-bound phase leaves its share of the SMs to the others.
 // RB_GROUPS / RB_GROUP_WAVE_PCT override (measurement aid).  Each group's grid covers `pct` % of one wave.
+// Round 2, 32 / 64 replicas (the per-GPU share of a 256-seed ensemble on 8 / 4 GPUs): 2 x 100 % 22.7 / 34.4 ms, 4 x 50 % 22.3 /
+// 33.6, 4 x 50 % with the latency-bound kernels at high launch priority (rb_engine::prio) 21.5 / 33.0; at 128 and 256
+// replicas the priorities gain nothing (57.2 vs 56.9, 106.4 vs 105.1): the SMs are full anyway.
 static void group_config(int R, int *n_groups, int *wave_pct) {
-    int ng = R >= 128 ? 4 : (R >= 32 ? 2 : 1), pct = R >= 128 ? 50 : 100;
+    int ng = R >= 32 ? 4 : 1, pct = R >= 32 ? 50 : 100;
     if (const char *s = getenv("RB_GROUPS")) ng = atoi(s);
     if (const char *s = getenv("RB_GROUP_WAVE_PCT")) pct = atoi(s);
     if (pct < 1) pct = 100;
@@ -374,12 +383,20 @@ static int setup_groups(rb_engine *e, int sms) {
     return 0;
 }
 
+// Every reset / state load starts a new flag epoch of the population-sharded exchange (shard.cuh).  The epoch lives in a
+// device word, not in the kernel arguments, so the captured graphs of sharded days stay valid.
+__global__ void k_set_word(uint32_t *p, uint32_t v) { *p = v; }
+static void bump_xepoch(rb_engine *e) {
+    e->xepoch++;
+    if (e->d_xepoch) { k_set_word<<<1, 1, 0, e->stream>>>(e->d_xepoch, e->xepoch); e->launches++; }
+}
+
 extern "C" int rb_reset(rb_engine *e, uint32_t seed) {
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaStreamSynchronize(e->stream));
     e->cfg.seed = seed;
     e->day = 0;
-    e->G.xepoch++;
+    bump_xepoch(e);
     if (init_population(e, seed, true)) return 1;
     if (e->has_ipc) {
         k_initial_state<<<e->G.R, 32, 0, e->stream>>>(e->G, e->ipc);
@@ -523,19 +540,27 @@ extern "C" int rb_set_schedule(rb_engine *e, int32_t day0, int32_t n, const rb_d
 // measured here: bit-exact, but no gain over plain graph edges for one replica (52.5 vs 50.7 us per day) and a loss for
 // ensembles (256 replicas 116.9 vs 104.2 ms: the early-scheduled CTAs of a group's next kernel hold SM slots that another
 // group's running kernel could use).  Removed again.)
+// `urgent`: the latency-bound kernels of a day (k_resolve, the day boundary) are launched with the highest priority, so
+// that their few CTAs are placed before the pending CTAs of another replica group's oversubscribed sweep / contact grids.
 template <typename K>
-static void launch_k(rb_engine *e, K kernel, dim3 grid, int threads, cudaStream_t st, const Eng &G) {
-    (void)e;
-    kernel<<<grid, threads, 0, st>>>(G);
+static void launch_k(rb_engine *e, K kernel, dim3 grid, int threads, cudaStream_t st, const Eng &G, bool urgent = false) {
+    if (!urgent || !e->prio) { kernel<<<grid, threads, 0, st>>>(G); return; }
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority; at[0].val.priority = e->prio_high;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, G);
+    if (err != cudaSuccess && e->launch_err == cudaSuccess) e->launch_err = err;
 }
 
 // The day boundary: one CTA per replica, or -- few replicas of a large population -- a cooperative launch of
 // wide_ctas co-resident CTAs per replica (boundary.cuh, Team).  kind: 0 = k_pre, 1 = k_post, 2 = k_between.
 static void launch_boundary(rb_engine *e, int kind, int R, cudaStream_t st, const Eng &G) {
     if (e->wide_ctas <= 1) {
-        if (kind == 0) launch_k(e, k_pre<false>, dim3(R), PRE_THREADS, st, G);
-        else if (kind == 1) launch_k(e, k_post<false>, dim3(R), PRE_THREADS, st, G);
-        else launch_k(e, k_between<false>, dim3(R), PRE_THREADS, st, G);
+        if (kind == 0) launch_k(e, k_pre<false>, dim3(R), PRE_THREADS, st, G, true);
+        else if (kind == 1) launch_k(e, k_post<false>, dim3(R), PRE_THREADS, st, G, true);
+        else launch_k(e, k_between<false>, dim3(R), PRE_THREADS, st, G, true);
         return;
     }
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
@@ -555,7 +580,7 @@ static void launch_segment(rb_engine *e, cudaStream_t st) {
     const Eng &G = e->G;
     launch_k(e, k_sweep, dim3(e->sweep_blocks, G.R), SW_THREADS, st, G);
     launch_k(e, k_expose, dim3(e->list_blocks, G.R), EX_THREADS, st, G);
-    launch_k(e, k_resolve<true>, dim3(e->resolve_blocks, G.R), 256, st, G);
+    launch_k(e, k_resolve<true>, dim3(e->resolve_blocks, G.R), 256, st, G, true);
     launch_boundary(e, 2, G.R, st, G);
 }
 
@@ -566,7 +591,7 @@ static void launch_group_segment(rb_engine *e, const ReplicaGroup &q, bool stagg
     launch_k(e, k_sweep, dim3(q.sweep_blocks, q.R), SW_THREADS, q.stream, G);
     launch_k(e, k_expose, dim3(q.list_blocks, q.R), EX_THREADS, q.stream, G);
     if (stagger_mark) cudaEventRecord(q.ev_stagger, q.stream);       // the next group starts its day here
-    launch_k(e, k_resolve<true>, dim3(q.resolve_blocks, q.R), 256, q.stream, G);
+    launch_k(e, k_resolve<true>, dim3(q.resolve_blocks, q.R), 256, q.stream, G, true);
     launch_boundary(e, 2, q.R, q.stream, G);
 }
 
@@ -581,7 +606,7 @@ static int build_graphs(rb_engine *e) {
                 CK(cudaStreamBeginCapture(q.stream, cudaStreamCaptureModeThreadLocal));
                 for (int i = 0; i < nseg; i++) launch_group_segment(e, q, false);
                 CK(cudaStreamEndCapture(q.stream, &gr));
-                CK(cudaGraphInstantiate(&q.graph[which], gr, 0));
+                CK(cudaGraphInstantiate(&q.graph[which], gr, e->prio ? cudaGraphInstantiateFlagUseNodePriority : 0));
                 CK(cudaGraphDestroy(gr));
             }
         e->have_graphs = true;
@@ -593,7 +618,7 @@ static int build_graphs(rb_engine *e) {
         CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
         for (int i = 0; i < nseg; i++) launch_segment(e, e->stream);
         CK(cudaStreamEndCapture(e->stream, &g));
-        CK(cudaGraphInstantiate(&e->graph[which], g, 0));
+        CK(cudaGraphInstantiate(&e->graph[which], g, e->prio ? cudaGraphInstantiateFlagUseNodePriority : 0));
         CK(cudaGraphDestroy(g));
     }
     e->have_graphs = true;
@@ -668,15 +693,12 @@ extern "C" int rb_shard_unique_id(uint8_t *out128) {
     return 0;
 }
 
-extern "C" int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const uint8_t *uid128, float exchange_capacity) {
+// What every way of joining shares: rank / size, the message capacities, the epoch word, the merge grid.
+static int shard_prepare(rb_engine *e, int32_t rank, int32_t nranks, float exchange_capacity) {
     if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) { snprintf(g_err, sizeof g_err, "bad rank %d / %d", rank, nranks); return 1; }
     if (e->G.R != 1) { snprintf(g_err, sizeof g_err, "population-sharded mode runs one replica (n_replicas = %d)", e->G.R); return 1; }
-    if (e->day != 0 || e->comm) { snprintf(g_err, sizeof g_err, "rb_shard_init must be the first call after rb_create"); return 1; }
-    if (load_nccl()) return 1;
+    if (e->day != 0 || e->comm || e->sharded) { snprintf(g_err, sizeof g_err, "rb_shard_init must be the first call after rb_create"); return 1; }
     CK(cudaSetDevice(e->cfg.device));
-    ncclUniqueId id; memcpy(&id, uid128, 128);
-    NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
-    e->comm_rank = rank; e->comm_size = nranks; e->sharded = true;
     Eng &G = e->G;
     // message capacities: this rank's share of the agents; a day's state changes / transmissions / tests / capacity
     // events are small fractions of it (peak day of the reference epidemic: 0.9 % / 0.5 % / 0.17 % / 0.08 % of the
@@ -688,8 +710,26 @@ extern "C" int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const u
     G.xcap_ev = (uint32_t)(share / 512) + 2048;
     G.xslot = xslot_bytes(G.xcap_q, G.xcap_ev, G.xcap_upd, G.xcap_succ);
     G.rank = rank; G.nranks = nranks;
+    e->comm_rank = rank; e->comm_size = nranks;
+    e->xepoch = 1;
+    if (dalloc(e, &e->d_xepoch, 1)) return 1;
+    CK(cudaMemcpy(e->d_xepoch, &e->xepoch, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    G.xepoch = e->d_xepoch;
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, e->cfg.device));
+    // (the sweep needs no adjustment: a rank's active list holds only the agents it owns, ~1 / nranks of the infected)
+    e->merge_blocks = prop.multiProcessorCount * 8 / nranks * nranks;      // a multiple of nranks: k_merge deals its blocks to the ranks
+    return 0;
+}
+
+extern "C" int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const uint8_t *uid128, float exchange_capacity) {
+    if (shard_prepare(e, rank, nranks, exchange_capacity)) return 1;
+    if (load_nccl()) return 1;
+    ncclUniqueId id; memcpy(&id, uid128, 128);
+    NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
+    e->sharded = true;
+    Eng &G = e->G;
     // Exchange through peer memory when every rank can map every other rank's buffer (CUDA IPC; one process per GPU on
-    // one NVLink box), else -- ranks in one process, no peer access, RB_SHARD_EXCHANGE=nccl -- through ncclAllGather.
+    // one NVLink box), else -- no peer access, RB_SHARD_EXCHANGE=nccl -- through ncclAllGather.
     {
         const char *mode = getenv("RB_SHARD_EXCHANGE");
         int ok = !(mode && strcmp(mode, "nccl") == 0);
@@ -727,7 +767,7 @@ extern "C" int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const u
         if (ok) {
             e->allocs.push_back(own);
             CK(cudaMemset(own, 0, own_bytes));
-            G.xbuf = own; G.xp2p = 1; G.xepoch = 1;
+            G.xbuf = own; G.xp2p = 1;
             // nobody may publish before every rank has cleared its flag line
             if (gather()) return 1;
         } else {
@@ -739,9 +779,63 @@ extern "C" int rb_shard_init(rb_engine *e, int32_t rank, int32_t nranks, const u
             CK(cudaMemset(G.xbuf, 0, G.xslot * nranks));
         }
     }
-    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, e->cfg.device));
-    // (the sweep needs no adjustment: a rank's active list holds only the agents it owns, ~1 / nranks of the infected)
-    e->merge_blocks = prop.multiProcessorCount * 8 / nranks * nranks;      // a multiple of nranks: k_merge deals its blocks to the ranks
+    return 0;
+}
+
+static int build_shard_graphs(rb_engine *e);
+
+// The ranks of ONE process (a host that drives several GPUs itself, or -- the tests on a single-GPU box -- several
+// engines on one device, each on its own stream): no NCCL, no CUDA IPC; a rank's message buffer is a plain device
+// pointer the others read directly (same device, or peer access enabled here).  Every engine must be driven by its own
+// host thread, or at least have its rb_step calls issued before anybody waits for one of them: a rank's day cannot end
+// before every other rank's sweep of that day has been launched.
+extern "C" int rb_shard_init_local(rb_engine **engines, int32_t nranks, float exchange_capacity) {
+    if (nranks < 1 || nranks > MAX_RANKS) { snprintf(g_err, sizeof g_err, "bad number of ranks %d", nranks); return 1; }
+    for (int k = 0; k < nranks; k++) {
+        for (int j = 0; j < k; j++) if (engines[j] == engines[k]) { snprintf(g_err, sizeof g_err, "rb_shard_init_local: the same engine twice"); return 1; }
+        if (engines[k]->G.N != engines[0]->G.N) { snprintf(g_err, sizeof g_err, "rb_shard_init_local: engines of different populations"); return 1; }
+    }
+    uint8_t *bufs[MAX_RANKS];
+    for (int k = 0; k < nranks; k++) {
+        rb_engine *e = engines[k];
+        if (shard_prepare(e, k, nranks, exchange_capacity)) return 1;
+        const size_t own_bytes = XFLAG_BYTES + 2 * e->G.xslot;
+        if (dalloc(e, &bufs[k], own_bytes)) return 1;
+        CK(cudaMemset(bufs[k], 0, own_bytes));
+    }
+    for (int k = 0; k < nranks; k++) {
+        rb_engine *e = engines[k];
+        CK(cudaSetDevice(e->cfg.device));
+        for (int j = 0; j < nranks; j++) {
+            const int dj = engines[j]->cfg.device;
+            if (dj != e->cfg.device) {
+                int can = 0; CK(cudaDeviceCanAccessPeer(&can, e->cfg.device, dj));
+                if (!can) { snprintf(g_err, sizeof g_err, "rb_shard_init_local: device %d cannot access device %d", e->cfg.device, dj); return 1; }
+                cudaError_t err = cudaDeviceEnablePeerAccess(dj, 0);
+                if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled) { snprintf(g_err, sizeof g_err, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(err)); return 1; }
+                cudaGetLastError();
+            }
+            e->G.xpeer[j] = bufs[j];
+        }
+        e->G.xbuf = bufs[k]; e->G.xp2p = 1; e->sharded = true;
+    }
+    // Everything a step needs is created NOW, while no rank is waiting for another: a first launch loads its kernel
+    // lazily and graph instantiation allocates, both of which may synchronise with the device -- which never returns
+    // while a peer's k_wait is spinning for the very rank that is stuck in the load.
+    for (int k = 0; k < nranks; k++) {
+        rb_engine *e = engines[k];
+        CK(cudaSetDevice(e->cfg.device));
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, k_pre<false>)); CK(cudaFuncGetAttributes(&fa, k_pre<true>));
+        CK(cudaFuncGetAttributes(&fa, k_post<false>)); CK(cudaFuncGetAttributes(&fa, k_post<true>));
+        CK(cudaFuncGetAttributes(&fa, k_between<false>)); CK(cudaFuncGetAttributes(&fa, k_between<true>));
+        CK(cudaFuncGetAttributes(&fa, k_sweep)); CK(cudaFuncGetAttributes(&fa, k_expose));
+        CK(cudaFuncGetAttributes(&fa, k_publish)); CK(cudaFuncGetAttributes(&fa, k_wait)); CK(cudaFuncGetAttributes(&fa, k_merge));
+        CK(cudaFuncGetAttributes(&fa, k_resolve<false>)); CK(cudaFuncGetAttributes(&fa, k_resolve<true>));
+        CK(cudaFuncGetAttributes(&fa, k_set_word));
+        if (!e->shard_timing && build_shard_graphs(e)) return 1;
+    }
+    for (int k = 0; k < nranks; k++) { CK(cudaSetDevice(engines[k]->cfg.device)); CK(cudaDeviceSynchronize()); }
     return 0;
 }
 
@@ -750,8 +844,8 @@ extern "C" int32_t rb_shard_nranks(rb_engine *e) { return e->G.nranks; }
 extern "C" int64_t rb_shard_message_bytes(rb_engine *e) { return e->sharded ? (int64_t)e->G.xslot : 0; }
 extern "C" int32_t rb_shard_exchange(rb_engine *e) { return !e->sharded ? 0 : (e->G.xp2p ? 2 : 1); }
 
-// One simulated day in sharded mode: sweep and contacts over the owned stripes, ONE all-gather of the ranks' messages,
-// then merge / resolve / day boundary replicated on every rank.
+// One simulated day in sharded mode: sweep and contacts over the owned stripes, the exchange of the ranks' messages
+// (flags in peer memory, or one all-gather), then merge / resolve / day boundary replicated on every rank.
 static int launch_day_sharded(rb_engine *e, bool last) {
     const Eng &G = e->G;
     cudaStream_t st = e->stream;
@@ -771,7 +865,24 @@ static int launch_day_sharded(rb_engine *e, bool last) {
     mark();
     launch_boundary(e, last ? 1 : 2, 1, st, G);
     mark();
-    e->launches += G.xp2p ? 7 : 5;
+    return 0;
+}
+#define SHARD_LAUNCHES_PER_DAY(G) ((G).xp2p ? 7 : 5)
+
+// Sharded days with the peer-memory exchange are pure kernel chains (the flag wait is a kernel too) that take no
+// per-day argument -- the day and the flag epoch are read from device memory -- so they are captured once, as graphs of
+// GRAPH_DAYS days and of one day, and replayed like the single-GPU segments.
+static int build_shard_graphs(rb_engine *e) {
+    for (int which = 0; which < 2; which++) {
+        const int nseg = which == 0 ? GRAPH_DAYS : 1;
+        cudaGraph_t g;
+        CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < nseg; i++) if (launch_day_sharded(e, false)) { cudaStreamEndCapture(e->stream, &g); return 1; }
+        CK(cudaStreamEndCapture(e->stream, &g));
+        CK(cudaGraphInstantiate(&e->sh_graph[which], g, 0));
+        CK(cudaGraphDestroy(g));
+    }
+    e->have_sh_graphs = true;
     return 0;
 }
 
@@ -803,9 +914,17 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     const Eng &G = e->G;
     const int R = G.R;
     if (e->sharded) {
+        const bool graphs = G.xp2p && !e->shard_timing;
+        if (graphs && !e->have_sh_graphs && build_shard_graphs(e)) return 1;
         CK(cudaEventRecord(e->ev0, e->stream));
         launch_boundary(e, 0, 1, e->stream, G); e->launches++;
-        for (int d = 0; d < n_days; d++) if (launch_day_sharded(e, d == n_days - 1)) return 1;
+        int mid = n_days - 1;
+        if (graphs) {
+            while (mid >= GRAPH_DAYS) { CK(cudaGraphLaunch(e->sh_graph[0], e->stream)); mid -= GRAPH_DAYS; }
+            while (mid > 0) { CK(cudaGraphLaunch(e->sh_graph[1], e->stream)); mid -= 1; }
+        } else for (; mid > 0; mid--) if (launch_day_sharded(e, false)) return 1;
+        if (launch_day_sharded(e, true)) return 1;
+        e->launches += (int64_t)n_days * SHARD_LAUNCHES_PER_DAY(G);
         CK(cudaEventRecord(e->ev1, e->stream));
         if (check_launches(e)) return 1;
         e->day += n_days;
@@ -840,7 +959,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
             Eng Gq = G; Gq.r0 = q.r0;
             launch_k(e, k_sweep, dim3(q.sweep_blocks, q.R), SW_THREADS, q.stream, Gq);
             launch_k(e, k_expose, dim3(q.list_blocks, q.R), EX_THREADS, q.stream, Gq);
-            launch_k(e, k_resolve<false>, dim3(q.resolve_blocks, q.R), 256, q.stream, Gq);
+            launch_k(e, k_resolve<false>, dim3(q.resolve_blocks, q.R), 256, q.stream, Gq, true);
             launch_boundary(e, 1, q.R, q.stream, Gq);
             e->launches += 4;
             CK(cudaEventRecord(q.ev_join, q.stream));
@@ -858,7 +977,7 @@ extern "C" int rb_step(rb_engine *e, int32_t n_days) {
     while (mid > 0) { CK(cudaGraphLaunch(e->graph[1], e->stream)); mid -= 1; e->launches += 4; }
     launch_k(e, k_sweep, dim3(e->sweep_blocks, R), SW_THREADS, e->stream, G);
     launch_k(e, k_expose, dim3(e->list_blocks, R), EX_THREADS, e->stream, G);
-    launch_k(e, k_resolve<false>, dim3(e->resolve_blocks, R), 256, e->stream, G);
+    launch_k(e, k_resolve<false>, dim3(e->resolve_blocks, R), 256, e->stream, G, true);
     launch_boundary(e, 1, R, e->stream, G);
     e->launches += 4;
     CK(cudaEventRecord(e->ev1, e->stream));
@@ -1193,6 +1312,7 @@ extern "C" int rb_load_state(rb_engine *e, const void *in, int64_t n_bytes) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     e->day = h.day; e->cfg.seed = h.seed;
-    e->G.xepoch++;
+    bump_xepoch(e);
+    CK(cudaStreamSynchronize(e->stream));
     return 0;
 }

@@ -19,6 +19,7 @@ __global__ void k_publish(Eng G) {
 // One warp, lane k watches rank k's flag: a single poller per peer keeps the NVLink request queues free for the data.
 __global__ void k_wait(Eng G) {
     RepCtr *c = &G.ctr[0];
+    if (c->problem) return;                                   // the run has failed already (sticky): do not wait a minute per remaining day
     if ((int)threadIdx.x < G.nranks) {
         const volatile uint32_t *flag = (const volatile uint32_t *)G.xpeer[threadIdx.x];
         const uint32_t want = xflag_value(G, c->day);

@@ -181,14 +181,14 @@ struct Eng {
     // pulls exactly the bytes each message holds over NVLink once the owner's flag says the day is complete.
     uint8_t *xbuf; size_t xslot;
     uint8_t *xpeer[MAX_RANKS];
-    int32_t xp2p; uint32_t xepoch;                 // xepoch: bumped by every reset / state load, keeps the flags monotonic
+    int32_t xp2p; const uint32_t *xepoch;          // *xepoch (a device word, so that captured graphs stay valid): bumped by every reset / state load, keeps the flags monotonic
     uint32_t xcap_q, xcap_ev, xcap_upd, xcap_succ;
 };
 
 // Ownership: stripes of 4096 agents (one warp step of the sweep) dealt round-robin, so every rank holds ~1/nranks of every age.
 #define XFLAG_BYTES 256
 #define SH_SHIFT 12
-__device__ __forceinline__ uint32_t xflag_value(const Eng &G, int day) { return G.xepoch * 65536u + (uint32_t)day + 1u; }
+__device__ __forceinline__ uint32_t xflag_value(const Eng &G, int day) { return *G.xepoch * 65536u + (uint32_t)day + 1u; }
 __device__ __forceinline__ bool owns(const Eng &G, uint32_t a) { return G.nranks == 1 || (int)((a >> SH_SHIFT) % (uint32_t)G.nranks) == G.rank; }
 
 // One rank's message: a RepCtr used as the header (count deltas of the sweep, list lengths) followed by the lists.

@@ -447,13 +447,24 @@ class Context:
     # -- extensions -------------------------------------------------------------------------------
     def run(self, days):
         """`days` x iterate() in one device-resident run (the per-day schedule is computed up front)."""
+        self._prepare_run(days)
+        self._launch_run(days)
+        self._finish_run()
+
+    # run() in three parts, for callers that drive several engines at once (sharded.run_local): everything that may
+    # allocate, upload or synchronise first; then the asynchronous launches; then the wait and the error check.
+    def _prepare_run(self, days):
         if self.day + days > self.max_days:
             raise ValueError('max_days=%d exceeded' % self.max_days)
         while len(self._plan) < self.day + days:
             self._plan_next_day()
         self._engine.set_schedule(self.day, self._plan[self.day:self.day + days])
+
+    def _launch_run(self, days):
         self._engine.step(days)
         self.day += days
+
+    def _finish_run(self):
         self._engine.sync()
         problems = self._engine.problem()
         if problems.any():                              # main.pyx:2017-2018

@@ -49,6 +49,42 @@ def shard_spec(dist=None, exchange_capacity=0.0, make_id=None):
     return (rank, n, exchange_unique_id(make_id, dist), exchange_capacity)
 
 
+def join_local(contexts, exchange_capacity=0.0):
+    """Several Contexts of THIS process (built from the same inputs, interventions and seed, not yet stepped) become the
+    ranks of one population-sharded simulation: rank k = contexts[k].  No NCCL, no other process: the engines read each
+    other's message buffers directly -- one device (each rank on its own stream; how a single-GPU box exercises the
+    multi-rank exchange) or several devices with peer access."""
+    _abi.shard_init_local([c._engine for c in contexts], exchange_capacity)
+    return contexts
+
+
+def run_local(contexts, days):
+    """Advance every local rank by `days`.  A rank's day ends only once every rank's sweep of that day has been launched,
+    and a rank that is waiting occupies the device: so everything that may allocate, upload or synchronise (planning,
+    contact tables, the schedule) is done for all ranks first, and only the asynchronous launches run side by side, one
+    host thread per rank."""
+    import threading
+    for c in contexts:
+        c._prepare_run(days)
+    for c in contexts:
+        c._engine.sync()
+    errors = []
+
+    def work(ctx):
+        try:
+            ctx._launch_run(days)
+            ctx._finish_run()
+        except Exception as exc:      # noqa: BLE001 -- re-raised below, in the caller's thread
+            errors.append(exc)
+    threads = [threading.Thread(target=work, args=(c,)) for c in contexts]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+
+
 def merge_agents(per_rank_agents):
     """Canonical agent records of the whole population from every rank's rb_read_agents: agent a is taken from the
     rank that owns it (day counters and severity are authoritative there)."""

@@ -50,6 +50,7 @@ def main():
     ap.add_argument('--seed0', type=int, default=1000)
     ap.add_argument('--processes', type=int, default=None)
     ap.add_argument('--configs', nargs='*', default=list(CONFIGS))
+    ap.add_argument('--suffix', default='', help="appended to the file name, e.g. _n256 for a higher-power ensemble")
     a = ap.parse_args()
     for name in a.configs:
         area, scenario, days = CONFIGS[name]
@@ -71,7 +72,7 @@ def main():
             extra = dict(age_count_override=helpers.small_population(80000), interventions=helpers.stress_interventions())
         series, t_iter, wall = ref_harness.run_ensemble(seeds, days=days, processes=a.processes,
                                                         area=area, scenario=scenario, variables=variables, **extra)
-        out = os.path.join(HERE, 'ref_ensemble_%s.npz' % name)
+        out = os.path.join(HERE, 'ref_ensemble_%s%s.npz' % (name, a.suffix))
         np.savez_compressed(
             out, mean=series.mean(axis=0), std=series.std(axis=0, ddof=1), n=len(seeds),
             names=np.array(ref_harness.series_names()), seeds=seeds,

@@ -152,3 +152,55 @@ def test_four_ranks_equal_oracle():
 def test_eight_ranks_equal_oracle():
     out = _run_sharded(8, 'default')
     _check_against_oracle(out, 8, 'default')
+
+
+# ---------------------------------------------------------------- several ranks on ONE GPU (rb_shard_init_local)
+# The ranks of one process, each engine on its own stream of the same device, read each other's message buffers through
+# plain device pointers: the flags, k_wait, k_merge over several messages and the ownership split run exactly as they do
+# across GPUs, so a single-GPU box checks the multi-rank exchange too.  A spawned process, so that
+# CUDA_DEVICE_MAX_CONNECTIONS (one hardware queue per rank: a waiting rank must never sit in front of a peer's kernels)
+# is in force when the CUDA context is created.
+def _local_worker(world, case, chunk, q):
+    try:
+        from reina_b200 import sharded
+        kw, days = _case(case)
+        ctxs = [helpers.make_context(helpers.cuda_library(), device=0, **kw) for _ in range(world)]
+        sharded.join_local(ctxs)
+        done = 0
+        while done < days:
+            n = min(chunk, days - done)
+            sharded.run_local(ctxs, n)
+            done += n
+        out = {}
+        for rank, ctx in enumerate(ctxs):
+            eng = ctx._engine
+            out[rank] = dict(series=ctx.series(0, days), agents=eng.read_agents(0), queue=np.sort(eng.read_queue(0)),
+                             avail=eng.read_available(0), launches=eng.launch_count(),
+                             msg_bytes=eng.lib.f['shard_message_bytes'](eng.h), exchange=eng.lib.f['shard_exchange'](eng.h))
+        q.put(out)
+    except Exception:
+        q.put(traceback.format_exc())
+
+
+def _run_local_ranks(world, case, chunk, monkeypatch):
+    monkeypatch.setenv('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+    monkeypatch.setenv('CUDA_MODULE_LOADING', 'EAGER')      # belt and braces: rb_shard_init_local loads its kernels itself
+    mpc = mp.get_context('spawn')
+    q = mpc.Queue()
+    p = mpc.Process(target=_local_worker, args=(world, case, chunk, q))
+    p.start()
+    try:
+        out = q.get(timeout=300)
+    finally:
+        p.join(timeout=30)
+        if p.is_alive():
+            p.kill()
+    assert not isinstance(out, str), 'local ranks failed:\n%s' % out
+    return out
+
+
+@pytest.mark.parametrize('world,case,chunk', [(2, 'stress', 31), (3, 'tracing', 1000), (4, 'default', 50), (8, 'stress', 1000)])
+def test_local_ranks_on_one_gpu_equal_oracle(monkeypatch, world, case, chunk):
+    out = _run_local_ranks(world, case, chunk, monkeypatch)
+    _check_against_oracle(out, world, case)
+    assert all(out[r]['exchange'] == 2 for r in range(world))
