@@ -183,6 +183,12 @@ int rb_problem(rb_engine *e, int32_t *out);
  * 2 incubation_period, 3 illness_period, 4 hospitalization_period, 5 icu_period, 6 onset_to_removed_period. */
 int rb_sample(rb_engine *e, int32_t what, int32_t age, int32_t severity, int32_t n, int32_t *out);
 
+/* The counter-based random block behind every draw (replaces RandomPool, simrandom.pyx:13-55), computed on the host by
+ * the function the kernels inline: words = 4 -> Philox4x32-10 with key (key, 0x5EEDB200) and counter ctr[0..3] (other
+ * widths are refused).  No device needed: the CPU tests pin the generator to the Random123 known-answer vectors through
+ * this call. */
+int rb_rng_block(int32_t words, uint32_t key, const uint32_t *ctr, uint32_t *out);
+
 /* Parity/debug exports. */
 int rb_read_agents(rb_engine *e, int32_t replica, rb_agent *out);
 int rb_read_queue(rb_engine *e, int32_t replica, int32_t *out, int32_t cap, int32_t *n);   /* test queue, in order */

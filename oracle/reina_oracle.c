@@ -812,6 +812,11 @@ int ro_step(rb_engine *e, int32_t n_days) {
 }
 int ro_sync(rb_engine *e) { (void)e; return 0; }
 int32_t ro_day(rb_engine *e) { return e->day; }
+int ro_rng_block(int32_t words, uint32_t key, const uint32_t *ctr, uint32_t *out) {
+    if (words == 4) { philox(key, KEY1, ctr[0], ctr[1], ctr[2], ctr[3], out); return 0; }
+    snprintf(g_err, sizeof g_err, "ro_rng_block: words must be 4");
+    return 1;
+}
 int32_t ro_row_len(rb_engine *e) { return e->row_len; }
 int ro_read_stats(rb_engine *e, int32_t day0, int32_t n, int32_t *out) {
     for (int ri = 0; ri < e->cfg.n_replicas; ri++)

@@ -84,7 +84,7 @@ CUDA_LIB_PATH = os.environ.get('REINA_B200_LIB') or os.path.join(_HERE, 'librein
 
 SYMBOLS = ['create', 'destroy', 'reset', 'set_initial_state', 'step_profiled', 'set_contact_table', 'set_schedule', 'step', 'sync', 'day',
            'snapshot', 'row_len', 'read_stats', 'read_moments', 'read_per_age', 'problem', 'sample', 'read_agents',
-           'read_queue', 'read_available', 'last_step_ms', 'launch_count', 'last_error']
+           'read_queue', 'read_available', 'last_step_ms', 'launch_count', 'last_error', 'rng_block']
 
 
 # population-sharded mode: exported by the CUDA library only (the sequential CPU oracle has no ranks)
@@ -149,6 +149,7 @@ class Library:
         f['read_per_age'].argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
         f['problem'].argtypes = [vp, C.POINTER(C.c_int32)]
         f['sample'].argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+        f['rng_block'].argtypes = [C.c_int32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         f['read_agents'].argtypes = [vp, C.c_int32, C.c_void_p]
         f['read_queue'].argtypes = [vp, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
         f['read_available'].argtypes = [vp, C.c_int32, C.POINTER(C.c_int32)]

@@ -1110,6 +1110,13 @@ extern "C" int rb_debug_phase_cycles(rb_engine *e, int32_t replica, long long *o
     RepCtr c; if (cudaMemcpy(&c, &e->G.ctr[replica], sizeof c, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
     memcpy(out16, c.dbg_t, sizeof c.dbg_t); return 0;
 }
+// The random blocks behind every draw, computed on the host by the very functions the kernels inline (rng.cuh): lets a
+// CPU-only test pin them to the published Random123 known-answer vectors.
+extern "C" int rb_rng_block(int32_t words, uint32_t key, const uint32_t *ctr, uint32_t *out) {
+    if (words == 4) { const u32x4 x = philox(key, ctr[0], ctr[1], ctr[2], ctr[3]); out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = x.w; return 0; }
+    snprintf(g_err, sizeof g_err, "rb_rng_block: words must be 4");
+    return 1;
+}
 extern "C" int32_t rb_row_len(rb_engine *e) { return e->G.row_len; }
 extern "C" float rb_last_step_ms(rb_engine *e) { return e->last_ms; }
 extern "C" int64_t rb_launch_count(rb_engine *e) { return e->launches; }

@@ -399,3 +399,35 @@ def test_serving_worker_forgets_old_jobs(oracle_lib):
     with pytest.raises(KeyError):
         w.results(jobs[0])
     w.close()
+
+
+# ---------------------------------------------------------------- the random blocks against Random123's known answers
+def _py_philox4(k0, k1, c):
+    M = 0xffffffff
+    c0, c1, c2, c3 = c
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & M, p1 & M, ((p0 >> 32) ^ c3 ^ k1) & M, p0 & M
+        k0, k1 = (k0 + 0x9E3779B9) & M, (k1 + 0xBB67AE85) & M
+    return [c0, c1, c2, c3]
+
+
+def test_random_blocks_match_random123_known_answers():
+    """(e) of north_star: simrandom replaced by counter-based Philox.  The algorithm lives in no dependency of the
+    reference (Random123, Salmon et al. 2011, is restated in rng.cuh / reina_oracle.c), so it is pinned here: the plain
+    Python restatement below reproduces the published kat_vectors of philox4x32-10, and both libraries (host build of
+    the very function the kernels inline) reproduce the restatement on the key layout the engine uses."""
+    M = 0xffffffff
+    assert _py_philox4(0, 0, (0, 0, 0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert _py_philox4(M, M, (M, M, M, M)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert _py_philox4(0xa4093822, 0x299f31d0, (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344)) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    import ctypes as C
+    rng = np.random.RandomState(5)
+    for lib in (helpers.oracle_library(), _abi.Library(_abi.CUDA_LIB_PATH, 'rb_')):
+        for _ in range(50):
+            key = int(rng.randint(0, 2 ** 32, dtype=np.uint64))
+            ctr = [int(v) for v in rng.randint(0, 2 ** 32, size=4, dtype=np.uint64)]
+            cbuf, out = (C.c_uint32 * 4)(*ctr), (C.c_uint32 * 4)()
+            assert lib.f['rng_block'](4, key, cbuf, out) == 0
+            assert list(out) == _py_philox4(key, 0x5EEDB200, ctr)
+        assert lib.f['rng_block'](2, 0, cbuf, out) != 0
