@@ -439,7 +439,9 @@ def main():
                       frac_dram=(traffic / (avg_ms / 1e3) / 1e9 / peak_gbs) if traffic else None,
                       design_bytes_per_launch=design / n_launch, frac_design=design / n_launch / (avg_ms / 1e3) / 1e9 / peak_gbs if avg_ms > 0 else None,
                       isolated=dict(avg_launch_ms=iso_ms, note='the same kernel over all %d replicas in ONE full-wave launch with the GPU to itself' % R,
-                                    frac=(nominal / D / (iso_ms / 1e3) / 1e9 / peak_gbs) if iso_ms > 0 else None),
+                                    frac=(nominal / D / (iso_ms / 1e3) / 1e9 / peak_gbs) if iso_ms > 0 else None,
+                                    # measured DRAM bytes of a day (the production launches of all groups together) over the isolated launch time
+                                    frac_dram=(traffic * n_launch / D / (iso_ms / 1e3) / 1e9 / peak_gbs) if traffic and iso_ms > 0 else None),
                       note='algorithmic bytes follow SURVEY.md 8(d), defined against the minimal hot state independently of the layout '
                            '(sweep 4 B/agent + 12 B/infected, contacts 8 B/contact); the list-based sweep never touches the 4 B/agent of the '
                            'idle population, hence frac_design (this design\'s own minimum) and frac_dram (measured DRAM bytes) beside it'),

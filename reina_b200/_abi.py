@@ -225,12 +225,17 @@ class Engine:
                                   _ptr(import_cum, C.c_float), C.byref(h)), 'create')
         self.h = h
         self.rank, self.nranks = 0, 1
+        self.half_joined = False         # set when a population-sharded join failed half-way
         self.row_len = lib.f['row_len'](h)
 
     def shard_init(self, rank, nranks, unique_id, exchange_capacity=0.0):
         """Join `nranks` engines (one per GPU / process) into one population-sharded simulation."""
         assert len(unique_id) == 128
-        self.lib.check(self.lib.f['shard_init'](self.h, rank, nranks, bytes(unique_id), exchange_capacity), 'shard_init')
+        try:
+            self.lib.check(self.lib.f['shard_init'](self.h, rank, nranks, bytes(unique_id), exchange_capacity), 'shard_init')
+        except EngineError:
+            self.half_joined = True      # the ownership split may already have changed: this engine must not step
+            raise
         self.rank, self.nranks = rank, nranks
 
     def save_state(self):
@@ -267,6 +272,8 @@ class Engine:
         self.lib.check(self.lib.f['set_schedule'](self.h, day0, len(params), arr), 'set_schedule')
 
     def step(self, n=1):
+        if self.half_joined:
+            raise EngineError('this engine was left half-joined by a failed population-sharded join: create a new Context')
         self.lib.check(self.lib.f['step'](self.h, n), 'step')
 
     def set_initial_state(self, ipc7):
@@ -389,7 +396,12 @@ def shard_init_local(engines, exchange_capacity=0.0):
     (rb_shard_init_local: plain device pointers instead of NCCL + CUDA IPC).  Step each from its own thread."""
     lib = engines[0].lib
     arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
-    lib.check(lib.f['shard_init_local'](arr, len(engines), exchange_capacity), 'shard_init_local')
+    try:
+        lib.check(lib.f['shard_init_local'](arr, len(engines), exchange_capacity), 'shard_init_local')
+    except EngineError:
+        for e in engines:
+            e.half_joined = True         # some ranks may already own only their stripes: none of them may step
+        raise
     for k, e in enumerate(engines):
         e.rank, e.nranks = k, len(engines)
 

@@ -431,3 +431,31 @@ def test_random_blocks_match_random123_known_answers():
             assert lib.f['rng_block'](4, key, cbuf, out) == 0
             assert list(out) == _py_philox4(key, 0x5EEDB200, ctr)
         assert lib.f['rng_block'](2, 0, cbuf, out) != 0
+
+
+def test_half_joined_engine_refuses_to_step():
+    """A population-sharded join that fails half-way may already have changed an engine's ownership split (it would
+    sweep only its stripes and still look like a whole population): such an engine must not step."""
+    class FailingLib:
+        f = {'shard_init': lambda *a: 1, 'shard_init_local': lambda *a: 1, 'step': lambda *a: 0}
+
+        def check(self, rc, what):
+            if rc:
+                raise _abi.EngineError(what + ' failed')
+
+    def fake_engine():
+        e = object.__new__(_abi.Engine)
+        e.lib, e.h, e.half_joined, e.rank, e.nranks = FailingLib(), None, False, 0, 1
+        return e
+    a = fake_engine()
+    with pytest.raises(_abi.EngineError):
+        a.shard_init(0, 2, b'x' * 128)
+    with pytest.raises(_abi.EngineError, match='half-joined'):
+        a.step(1)
+    b, c = fake_engine(), fake_engine()
+    b.step(1)                                   # a healthy engine steps
+    with pytest.raises(_abi.EngineError):
+        _abi.shard_init_local([b, c])
+    for e in (b, c):
+        with pytest.raises(_abi.EngineError, match='half-joined'):
+            e.step(1)
