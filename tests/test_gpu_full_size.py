@@ -47,34 +47,50 @@ def test_ensemble_statistics_match_reference(cuda_lib, gold_name, area, scenario
         assert abs(z[-1, names.index(s)]) < 3.0, (s, z[-1, names.index(s)])
 
 
-def test_high_power_statistics_hus_default(cuda_lib):
-    """BASELINE configs[1] / [3] at higher statistical power: 256 CUDA replicas (the bench's own ensemble size) against
-    256 seeds of the UNMODIFIED reference engine (tests/golden/make_golden.py --seeds 256 --suffix _n256).  With 64 + 64
-    seeds a modelling error of ~1.5 % in a total hides inside 3 SE; at 256 + 256 one standard error of the day-180 totals is
-    0.5-0.75 %, which is what
-    keeps the accelerations shared by oracle and engine (thinning, tabulated contact count, 24-bit row uniforms) honest."""
-    gold = np.load(os.path.join(GOLD, 'ref_ensemble_hus_default_n256.npz'))
-    assert int(gold['n']) == 256
-    ctx = helpers.make_context(cuda_lib, area='HUS', seed=909090, n_replicas=256, max_days=181)
-    ctx.run(180)
-    mine = helpers.series_matrix(ctx)
-    ctx.close()
+HIGH_POWER = [
+    # golden file, area, scenario, base seed of the 256 replicas
+    ('hus_default_n256', 'HUS', None, 909090),                       # BASELINE configs[1] / [3]
+    ('hus_hammer_and_dance_n256', 'HUS', 'hammer-and-dance', 919191),   # configs[2]: contact tracing 30 -> 60 % + mobility
+    ('hus_mitigation_n256', 'HUS', 'mitigation', 929292),            # configs[2]: capacity building + mobility limits
+]
+
+
+def high_power_report(mine, gold_name):
+    """256 runs of ours (rows [256, days, series]) against 256 seeds of the UNMODIFIED reference engine: the statistics the
+    test asserts on, shared with tests/golden/precheck_high_power.py (which computes `mine` with the sequential oracle
+    from the very seeds the GPU test uses -- bit-identical rows -- so the thresholds are known to hold before a GPU run)."""
+    gold = np.load(os.path.join(GOLD, 'ref_ensemble_%s.npz' % gold_name))
+    assert int(gold['n']) == 256 and mine.shape[0] == 256
     names = list(gold['names'])
     assert names == helpers.series_names()
     z, exact = zscores(mine, gold)
     assert not exact.any(), 'deterministic series differ: %s' % sorted({names[j] for j in np.argwhere(exact)[:, 1]})
     frac3, frac2 = (np.abs(z) > 3).mean(), (np.abs(z) > 2).mean()
     worst = np.unravel_index(np.abs(z).argmax(), z.shape)
-    print('hus_default 256 + 256 seeds: cells beyond 3 SE %.4f, beyond 2 SE %.4f (a normal gives 0.0027 / 0.0455), worst |z| %.2f (%s day %d)'
-          % (frac3, frac2, np.abs(z).max(), names[worst[1]], worst[0]))
+    print('%s, 256 + 256 seeds: cells beyond 3 SE %.4f, beyond 2 SE %.4f (a normal gives 0.0027 / 0.0455), worst |z| %.2f (%s day %d)'
+          % (gold_name, frac3, frac2, np.abs(z).max(), names[worst[1]], worst[0]))
     assert frac3 < 0.01 and frac2 < 0.10
     assert np.abs(z).max() < 4.5
     m, g = mine.mean(0)[-1], gold['mean'][-1]
     for s in ('all_infected', 'dead', 'all_detected', 'recovered', 'cum_icu'):
         j = names.index(s)
         rel = (m[j] - g[j]) / g[j]
-        print('   day 180 %-14s cuda %12.1f  reference %12.1f  (%+.2f %%, z %+.2f)' % (s, m[j], g[j], 100 * rel, z[-1, j]))
+        print('   day 180 %-14s ours %12.1f  reference %12.1f  (%+.2f %%, z %+.2f)' % (s, m[j], g[j], 100 * rel, z[-1, j]))
         assert abs(z[-1, j]) < 3.0 and abs(rel) < 0.025, (s, rel, z[-1, j])
+
+
+@pytest.mark.parametrize('gold_name,area,scenario,seed', HIGH_POWER)
+def test_high_power_statistics(cuda_lib, gold_name, area, scenario, seed):
+    """Higher statistical power than the 64-seed tests above: 256 CUDA replicas (the bench's own ensemble size) against 256
+    seeds of the UNMODIFIED reference engine (tests/golden/make_golden.py --seeds 256 --seed0 50000 --suffix _n256).  With
+    64 + 64 seeds a modelling error of ~1.5 % in a total hides inside 3 SE; at 256 + 256 one standard error of the day-180
+    totals is 0.5-0.75 %, which is what keeps the accelerations shared by oracle and engine (thinning, tabulated contact
+    count, 24-bit row uniforms) honest -- for the default run, for contact tracing and for capacity building."""
+    ctx = helpers.make_context(cuda_lib, area=area, scenario=scenario, seed=seed, n_replicas=256, max_days=181)
+    ctx.run(180)
+    mine = helpers.series_matrix(ctx)
+    ctx.close()
+    high_power_report(mine, gold_name)
 
 
 def test_full_size_properties(cuda_lib):
