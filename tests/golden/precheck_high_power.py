@@ -17,8 +17,10 @@ import helpers  # noqa: E402
 
 
 def _run(job):
-    area, scenario, seed = job
-    ctx = helpers.make_context(helpers.oracle_library(), area=area, scenario=scenario, seed=seed, max_days=181)
+    import test_gpu_full_size as T
+    area, scenario, seed, variables = job
+    ctx = helpers.make_context(helpers.oracle_library(), area=area, scenario=scenario, seed=seed, max_days=181,
+                               variables=T.high_power_variables(variables))
     ctx.run(180)
     return helpers.series_matrix(ctx)[0]
 
@@ -26,11 +28,11 @@ def _run(job):
 def main():
     import test_gpu_full_size as T
     want = set(sys.argv[1:])
-    for gold_name, area, scenario, seed in T.HIGH_POWER:
+    for gold_name, area, scenario, seed, variables in T.HIGH_POWER:
         if want and gold_name not in want:
             continue
         with ProcessPoolExecutor(os.cpu_count() or 1) as ex:
-            mine = np.stack(list(ex.map(_run, [(area, scenario, seed + r) for r in range(256)])))
+            mine = np.stack(list(ex.map(_run, [(area, scenario, seed + r, variables) for r in range(256)])))
         T.high_power_report(mine, gold_name)
         print('%s: the assertions of the GPU test hold' % gold_name, flush=True)
 

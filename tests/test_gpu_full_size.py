@@ -48,11 +48,24 @@ def test_ensemble_statistics_match_reference(cuda_lib, gold_name, area, scenario
 
 
 HIGH_POWER = [
-    # golden file, area, scenario, base seed of the 256 replicas
-    ('hus_default_n256', 'HUS', None, 909090),                       # BASELINE configs[1] / [3]
-    ('hus_hammer_and_dance_n256', 'HUS', 'hammer-and-dance', 919191),   # configs[2]: contact tracing 30 -> 60 % + mobility
-    ('hus_mitigation_n256', 'HUS', 'mitigation', 929292),            # configs[2]: capacity building + mobility limits
+    # golden file, area, scenario, base seed of the 256 replicas, variable overrides
+    ('hus_default_n256', 'HUS', None, 909090, None),                       # BASELINE configs[1] / [3]
+    ('hus_hammer_and_dance_n256', 'HUS', 'hammer-and-dance', 919191, None),   # configs[2]: contact tracing 30 -> 60 % + mobility
+    ('hus_mitigation_n256', 'HUS', 'mitigation', 929292, None),            # configs[2]: capacity building + mobility limits
+    ('hus_summer_boogie_n256', 'HUS', 'summer-boogie', 939393, None),
+    ('hus_looser_restrictions_n256', 'HUS', 'looser-restrictions-to-start-with', 949494, None),   # configs[2]: every limit-mobility value halved
+    ('hus_initial_state_n256', 'HUS', None, 959595, 'initial_state'),      # Population.set_initial_state, start 2020-04-01
+    ('varsinais_suomi_default_n256', 'Varsinais-Suomi', None, 969696, None),   # configs[0]
 ]
+
+
+def high_power_variables(key):
+    if key is None:
+        return None
+    from test_oracle_pinned import INITIAL_STATE_VARIABLES
+    v = helpers.inputs.default_variables()
+    v.update(INITIAL_STATE_VARIABLES)
+    return v
 
 
 def high_power_report(mine, gold_name):
@@ -79,14 +92,15 @@ def high_power_report(mine, gold_name):
         assert abs(z[-1, j]) < 3.0 and abs(rel) < 0.025, (s, rel, z[-1, j])
 
 
-@pytest.mark.parametrize('gold_name,area,scenario,seed', HIGH_POWER)
-def test_high_power_statistics(cuda_lib, gold_name, area, scenario, seed):
+@pytest.mark.parametrize('gold_name,area,scenario,seed,variables', HIGH_POWER)
+def test_high_power_statistics(cuda_lib, gold_name, area, scenario, seed, variables):
     """Higher statistical power than the 64-seed tests above: 256 CUDA replicas (the bench's own ensemble size) against 256
     seeds of the UNMODIFIED reference engine (tests/golden/make_golden.py --seeds 256 --seed0 50000 --suffix _n256).  With
     64 + 64 seeds a modelling error of ~1.5 % in a total hides inside 3 SE; at 256 + 256 one standard error of the day-180
     totals is 0.5-0.75 %, which is what keeps the accelerations shared by oracle and engine (thinning, tabulated contact
-    count, 24-bit row uniforms) honest -- for the default run, for contact tracing and for capacity building."""
-    ctx = helpers.make_context(cuda_lib, area=area, scenario=scenario, seed=seed, n_replicas=256, max_days=181)
+    count, 24-bit row uniforms) honest -- for every configuration the 64-seed tests above cover."""
+    ctx = helpers.make_context(cuda_lib, area=area, scenario=scenario, seed=seed, n_replicas=256, max_days=181,
+                               variables=high_power_variables(variables))
     ctx.run(180)
     mine = helpers.series_matrix(ctx)
     ctx.close()
