@@ -459,3 +459,42 @@ def test_half_joined_engine_refuses_to_step():
     for e in (b, c):
         with pytest.raises(_abi.EngineError, match='half-joined'):
             e.step(1)
+
+
+def test_run_local_prepares_every_rank_before_any_launch():
+    """sharded.run_local: planning, uploads and the schedule of ALL ranks first (they may synchronise with the device, and
+    a rank that is already waiting for a peer occupies it), only then the launches, each on a thread of its own; an error
+    on one rank's thread surfaces in the caller."""
+    import threading
+    from reina_b200 import sharded
+    log, lock = [], threading.Lock()
+
+    class FakeEngine:
+        def sync(self):
+            with lock:
+                log.append('sync')
+
+    class FakeCtx:
+        def __init__(self, k, fail=False):
+            self.k, self.fail, self._engine = k, fail, FakeEngine()
+
+        def _prepare_run(self, days):
+            with lock:
+                log.append('prepare')
+
+        def _launch_run(self, days):
+            with lock:
+                log.append('launch')
+            if self.fail:
+                raise model.SimulationFailed('Other failure')
+
+        def _finish_run(self):
+            with lock:
+                log.append('finish')
+    ctxs = [FakeCtx(k) for k in range(4)]
+    sharded.run_local(ctxs, 7)
+    assert log[:8] == ['prepare'] * 4 + ['sync'] * 4            # every rank prepared and idle ...
+    assert sorted(log[8:]) == ['finish'] * 4 + ['launch'] * 4   # ... before the first launch
+    del log[:]
+    with pytest.raises(model.SimulationFailed):
+        sharded.run_local([FakeCtx(0), FakeCtx(1, fail=True)], 3)
